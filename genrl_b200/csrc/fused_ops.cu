@@ -1,0 +1,815 @@
+// Row-wise fused kernels of the GenRL hot path (sm_100a): LayerNorm+SiLU, GRU gates, categorical
+// straight-through sample, balanced KL, two-hot head, Normal actor head, lambda-return, MSE image loss.
+// All are HBM-bound: one warp per row, coalesced loads, fp32 math, activations stored as T (fp32 | bf16).
+// Each forward has a hand-written backward (no autograd inside the library).
+#include "common.cuh"
+
+namespace genrl {
+
+#define DISPATCH_T(dtype, ...)                                     \
+  do {                                                             \
+    if ((dtype) == GENRL_F32) { using T = float; __VA_ARGS__; }    \
+    else if ((dtype) == GENRL_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { set_error("bad dtype %d", (int)(dtype)); return 1; }    \
+  } while (0)
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+
+static inline int row_grid(long long rows, int cap = 148 * 8) {
+  long long g = (rows + WARPS - 1) / WARPS;
+  if (g < 1) g = 1;
+  return (int)(g > cap ? cap : g);
+}
+
+// =================================================================================================
+// LayerNorm (+SiLU)     reference: NormLayer dreamer_utils.py:844-859 (eps 1e-5), ImgChLayerNorm :1031-1040 (eps 1e-3)
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(THREADS) ln_act_fwd_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int act, T* __restrict__ y,
+                                                             long long ldy, float* __restrict__ stats, long long M, int D) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
+    const T* xr = x + row * ldx;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s += to_f32(xr[c]);
+    const float mean = warp_sum(s) / D;
+    float v = 0.f;
+    for (int c = lane; c < D; c += 32) { float d = to_f32(xr[c]) - mean; v += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / D + eps);
+    T* yr = y + row * ldy;
+    for (int c = lane; c < D; c += 32) {
+      float a = (to_f32(xr[c]) - mean) * rstd * gamma[c] + beta[c];
+      yr[c] = from_f32<T>(act == GENRL_ACT_SILU ? siluf_(a) : a);
+    }
+    if (stats && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+  }
+}
+
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)),  g = dy * act'(gamma*xhat+beta)
+// dgamma += sum_rows g*xhat ; dbeta += sum_rows g ; dlin_bias += sum_rows dx   (all optional, fp32 atomics)
+template <typename T>
+__global__ void __launch_bounds__(THREADS) ln_act_bwd_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlin_bias,
+                                                             long long M, int D) {
+  extern __shared__ float sm[];        // [3][D] column partials
+  float* s_dg = sm; float* s_db = sm + D; float* s_dl = sm + 2 * D;
+  const bool need_cols = dgamma != nullptr || dlin_bias != nullptr;
+  if (need_cols) { for (int i = threadIdx.x; i < 3 * D; i += THREADS) sm[i] = 0.f; __syncthreads(); }
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
+    const T* xr = x + row * ldx; const T* dyr = dy + row * lddy;
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < D; c += 32) {
+      float xh = (to_f32(xr[c]) - mean) * rstd;
+      float g = to_f32(dyr[c]);
+      if (act == GENRL_ACT_SILU) g *= silu_gradf_(xh * gamma[c] + beta[c]);
+      float gh = g * gamma[c];
+      s1 += gh; s2 += gh * xh;
+    }
+    s1 = warp_sum(s1) / D; s2 = warp_sum(s2) / D;
+    T* dxr = dx + row * lddx;
+    for (int c = lane; c < D; c += 32) {
+      float xh = (to_f32(xr[c]) - mean) * rstd;
+      float g = to_f32(dyr[c]);
+      if (act == GENRL_ACT_SILU) g *= silu_gradf_(xh * gamma[c] + beta[c]);
+      float d = rstd * (g * gamma[c] - s1 - xh * s2);
+      dxr[c] = from_f32<T>(d);
+      if (need_cols) {
+        if (dgamma) { atomicAdd(&s_dg[c], g * xh); atomicAdd(&s_db[c], g); }
+        if (dlin_bias) atomicAdd(&s_dl[c], d);
+      }
+    }
+  }
+  if (need_cols) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += THREADS) {
+      if (dgamma) { atomicAdd(&dgamma[c], s_dg[c]); atomicAdd(&dbeta[c], s_db[c]); }
+      if (dlin_bias) atomicAdd(&dlin_bias[c], s_dl[c]);
+    }
+  }
+}
+
+// column sum: out[c] += sum_rows x[r,c]   (bias gradients of Linear layers not followed by LN)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, long long M, int D, long long rows_per_block) {
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  for (int c = blockIdx.x * 256 + threadIdx.x; c < D; c += gridDim.x * 256) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += to_f32(x[r * ldx + c]);
+    atomicAdd(&out[c], s);
+  }
+}
+
+// =================================================================================================
+// GRU cell tail     reference: GRUCell.forward dreamer_utils.py:771-785 (LayerNorm(3D) eps 1e-5, update_bias -1, tanh)
+//   z[M,3D] = W [x|h]   ->   p = LN(z);  r = sig(p_r); cand = tanh(r * p_c); u = sig(p_u - 1);  h' = u*cand + (1-u)*h
+// =================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(THREADS) gru_fwd_kernel(const T* __restrict__ z, long long ldz, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ hprev, long long ldh,
+                                                          float* __restrict__ hout, long long ldho, T* __restrict__ hout_t, long long ldht,
+                                                          float* __restrict__ stats, long long M, int D) {
+  const int lane = threadIdx.x & 31;
+  const int D3 = 3 * D;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
+    const T* zr = z + row * ldz;
+    float s = 0.f;
+    for (int c = lane; c < D3; c += 32) s += to_f32(zr[c]);
+    const float mean = warp_sum(s) / D3;
+    float v = 0.f;
+    for (int c = lane; c < D3; c += 32) { float d = to_f32(zr[c]) - mean; v += d * d; }
+    const float rstd = 1.0f / sqrtf(warp_sum(v) / D3 + 1e-5f);
+    for (int j = lane; j < D; j += 32) {
+      float pr = (to_f32(zr[j]) - mean) * rstd * gamma[j] + beta[j];
+      float pc = (to_f32(zr[D + j]) - mean) * rstd * gamma[D + j] + beta[D + j];
+      float pu = (to_f32(zr[2 * D + j]) - mean) * rstd * gamma[2 * D + j] + beta[2 * D + j];
+      float r = sigmoidf_(pr), cand = tanhf(r * pc), u = sigmoidf_(pu - 1.0f);
+      float h = hprev[row * ldh + j];
+      float hn = u * cand + (1.0f - u) * h;
+      hout[row * ldho + j] = hn;
+      if (hout_t) hout_t[row * ldht + j] = from_f32<T>(hn);
+    }
+    if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS) gru_bwd_kernel(const float* __restrict__ dh, long long lddh, const T* __restrict__ z, long long ldz,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
+                                                          T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int D) {
+  extern __shared__ float sm[];        // [2][3D]
+  const int D3 = 3 * D;
+  float* s_dg = sm; float* s_db = sm + D3;
+  if (dgamma) { for (int i = threadIdx.x; i < 2 * D3; i += THREADS) sm[i] = 0.f; __syncthreads(); }
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
+    const T* zr = z + row * ldz;
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float s1 = 0.f, s2 = 0.f;
+    // pass 1: gate gradients -> reductions for the LN backward
+    for (int j = lane; j < D; j += 32) {
+      float xr_ = (to_f32(zr[j]) - mean) * rstd, xc = (to_f32(zr[D + j]) - mean) * rstd, xu = (to_f32(zr[2 * D + j]) - mean) * rstd;
+      float pr = xr_ * gamma[j] + beta[j], pc = xc * gamma[D + j] + beta[D + j], pu = xu * gamma[2 * D + j] + beta[2 * D + j];
+      float r = sigmoidf_(pr), cand = tanhf(r * pc), u = sigmoidf_(pu - 1.0f);
+      float h = hprev[row * ldh + j];
+      float g = dh[row * lddh + j];
+      float drc = g * u * (1.0f - cand * cand);
+      float gpr = drc * pc * r * (1.0f - r), gpc = drc * r, gpu = g * (cand - h) * u * (1.0f - u);
+      float a = gpr * gamma[j], b = gpc * gamma[D + j], c = gpu * gamma[2 * D + j];
+      s1 += a + b + c; s2 += a * xr_ + b * xc + c * xu;
+    }
+    s1 = warp_sum(s1) / D3; s2 = warp_sum(s2) / D3;
+    for (int j = lane; j < D; j += 32) {
+      float xr_ = (to_f32(zr[j]) - mean) * rstd, xc = (to_f32(zr[D + j]) - mean) * rstd, xu = (to_f32(zr[2 * D + j]) - mean) * rstd;
+      float pr = xr_ * gamma[j] + beta[j], pc = xc * gamma[D + j] + beta[D + j], pu = xu * gamma[2 * D + j] + beta[2 * D + j];
+      float r = sigmoidf_(pr), cand = tanhf(r * pc), u = sigmoidf_(pu - 1.0f);
+      float h = hprev[row * ldh + j];
+      float g = dh[row * lddh + j];
+      float drc = g * u * (1.0f - cand * cand);
+      float gpr = drc * pc * r * (1.0f - r), gpc = drc * r, gpu = g * (cand - h) * u * (1.0f - u);
+      dz[row * lddz + j] = from_f32<T>(rstd * (gpr * gamma[j] - s1 - xr_ * s2));
+      dz[row * lddz + D + j] = from_f32<T>(rstd * (gpc * gamma[D + j] - s1 - xc * s2));
+      dz[row * lddz + 2 * D + j] = from_f32<T>(rstd * (gpu * gamma[2 * D + j] - s1 - xu * s2));
+      if (dhprev) dhprev[row * lddhp + j] = g * (1.0f - u);
+      if (dgamma) {
+        atomicAdd(&s_dg[j], gpr * xr_); atomicAdd(&s_dg[D + j], gpc * xc); atomicAdd(&s_dg[2 * D + j], gpu * xu);
+        atomicAdd(&s_db[j], gpr); atomicAdd(&s_db[D + j], gpc); atomicAdd(&s_db[2 * D + j], gpu);
+      }
+    }
+  }
+  if (dgamma) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < D3; c += THREADS) { atomicAdd(&dgamma[c], s_dg[c]); atomicAdd(&dbeta[c], s_db[c]); }
+  }
+}
+
+// =================================================================================================
+// Categorical latent   reference: OneHotDist dreamer_utils.py:177-197, get_dist :410-416
+//   pi = normalise(0.99 softmax(logit) + 0.01/K);  idx = argmax(pi / q), q ~ Exp(1);  stoch = one_hot(idx)
+// One warp per (row, latent); lanes stride over the K classes.
+// =================================================================================================
+struct CatProbs { float p, u, pi; };   // softmax prob, unimix, normalised
+
+template <int MAXK_PER_LANE>
+__device__ __forceinline__ void cat_probs(const float* lg, int K, int lane, float* p, float* pi, float& usum) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) { int k = lane + 32 * i; if (k < K) mx = fmaxf(mx, lg[k]); }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) { int k = lane + 32 * i; p[i] = k < K ? expf(lg[k] - mx) : 0.f; s += p[i]; }
+  s = warp_sum(s);
+  float us = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) {
+    int k = lane + 32 * i;
+    p[i] = p[i] / s;
+    pi[i] = k < K ? 0.99f * p[i] + (1.0f - 0.99f) * 1.0f / K : 0.f;
+    us += pi[i];
+  }
+  usum = warp_sum(us);
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) pi[i] = pi[i] / usum;
+}
+
+// given d(loss)/d(pi) (per lane) returns d(loss)/d(logit) through normalise -> unimix -> softmax
+template <int MAXK_PER_LANE>
+__device__ __forceinline__ void cat_probs_bwd(const float* p, const float* pi, float usum, const float* dpi, float* dl) {
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) dot += dpi[i] * pi[i];
+  dot = warp_sum(dot);
+  float dp[MAXK_PER_LANE];
+  float dot2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) { dp[i] = 0.99f * (dpi[i] - dot) / usum; dot2 += dp[i] * p[i]; }
+  dot2 = warp_sum(dot2);
+#pragma unroll
+  for (int i = 0; i < MAXK_PER_LANE; ++i) dl[i] = p[i] * (dp[i] - dot2);
+}
+
+constexpr int KPL = 2;   // classes per lane -> K <= 64
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS) cat_sample_fwd_kernel(const float* __restrict__ logit, const float* __restrict__ noise,
+                                                                 unsigned long long seed, unsigned long long offset, int sample,
+                                                                 T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
+                                                                 long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S, int K) {
+  const int lane = threadIdx.x & 31;
+  const long long total = rows * S;
+  for (long long g = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * WARPS) {
+    const float* lg = logit + g * K;
+    float p[KPL], pi[KPL], usum;
+    cat_probs<KPL>(lg, K, lane, p, pi, usum);
+    float best = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) {
+        float score;
+        if (sample) {
+          float q;
+          if (noise) q = noise[g * K + k];
+          else {
+            uint4 r = philox4x32(make_uint4((uint32_t)(g * K + k), (uint32_t)((g * K + k) >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            q = -logf(u32_to_unit_open(r.x));
+          }
+          score = pi[i] / q;
+        } else {
+          score = logf(pi[i]);
+        }
+        if (score > best) { best = score; bi = k; }
+      }
+    }
+    // warp argmax, first index wins on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    const long long row = g / S; const int s = (int)(g % S);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) {
+        float v = k == bi ? 1.f : 0.f;
+        if (stoch) stoch[row * ld_stoch + s * K + k] = from_f32<T>(v);
+        if (stoch32) stoch32[row * ld_stoch32 + s * K + k] = v;
+      }
+    }
+    if (idx_out && lane == 0) idx_out[g] = bi;
+  }
+}
+
+// straight-through backward: dlogit (+)= J_pi^T dstoch   (sample) or J_logpi^T dstoch (mode)
+template <typename T>
+__global__ void __launch_bounds__(THREADS) cat_sample_bwd_kernel(const float* __restrict__ logit, const T* __restrict__ dstoch, long long ld_ds,
+                                                                 int sample, float* __restrict__ dlogit, int accumulate, long long rows, int S, int K) {
+  const int lane = threadIdx.x & 31;
+  const long long total = rows * S;
+  for (long long g = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * WARPS) {
+    float p[KPL], pi[KPL], usum, dpi[KPL], dl[KPL];
+    cat_probs<KPL>(logit + g * K, K, lane, p, pi, usum);
+    const long long row = g / S; const int s = (int)(g % S);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      int k = lane + 32 * i;
+      float d = k < K ? to_f32(dstoch[row * ld_ds + s * K + k]) : 0.f;
+      dpi[i] = sample ? d : (k < K ? d / pi[i] : 0.f);
+    }
+    cat_probs_bwd<KPL>(p, pi, usum, dpi, dl);
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      int k = lane + 32 * i;
+      if (k < K) { float* o = dlogit + g * K + k; *o = accumulate ? *o + dl[i] : dl[i]; }
+    }
+  }
+}
+
+// =================================================================================================
+// Balanced KL with free bits + entropies   reference: EnsembleRSSM.kl_loss dreamer_utils.py:534-555, dreamer.py:249-250
+//   value[r] = KL(lhs || rhs) summed over S;  loss = mix*mean(max(value,free)) + (1-mix)*mean(max(value,free))
+//   (the two terms differ only in where the gradient flows).  out[0]=loss, out[1]=mean(value), out[2]=mean ent(lhs), out[3]=mean ent(rhs)
+// One warp per row; loops the S latents.
+// =================================================================================================
+__global__ void __launch_bounds__(THREADS) kl_fwd_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, float free_bits,
+                                                         float* __restrict__ value, float* __restrict__ out, long long rows, int S, int K) {
+  const int lane = threadIdx.x & 31;
+  float acc_loss = 0.f, acc_val = 0.f, acc_el = 0.f, acc_er = 0.f;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
+    float kl = 0.f, el = 0.f, er = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float p[KPL], P[KPL], q[KPL], Q[KPL], us;
+      cat_probs<KPL>(lhs + (row * S + s) * K, K, lane, p, P, us);
+      cat_probs<KPL>(rhs + (row * S + s) * K, K, lane, q, Q, us);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        if (lane + 32 * i < K) {
+          float lp = logf(P[i]), lq = logf(Q[i]);
+          kl += P[i] * (lp - lq); el -= P[i] * lp; er -= Q[i] * lq;
+        }
+      }
+    }
+    kl = warp_sum(kl); el = warp_sum(el); er = warp_sum(er);
+    if (lane == 0) { value[row] = kl; acc_loss += fmaxf(kl, free_bits); acc_val += kl; acc_el += el; acc_er += er; }
+  }
+  if (lane == 0) {
+    const float inv = 1.0f / rows;
+    atomicAdd(&out[0], acc_loss * inv); atomicAdd(&out[1], acc_val * inv);
+    atomicAdd(&out[2], acc_el * inv); atomicAdd(&out[3], acc_er * inv);
+  }
+}
+
+// dlhs = gscale*w_lhs/rows * 1[value>free] * dKL/dlhs ; drhs likewise with w_rhs.  (w = mix / 1-mix)
+__global__ void __launch_bounds__(THREADS) kl_bwd_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, const float* __restrict__ value,
+                                                         float free_bits, float w_lhs, float w_rhs, const float* __restrict__ gscale,
+                                                         float* __restrict__ dlhs, float* __restrict__ drhs, long long rows, int S, int K) {
+  const int lane = threadIdx.x & 31;
+  const float gs = gscale ? *gscale : 1.0f;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
+    const float v = value[row];
+    // torch.maximum passes the gradient where value > free (half of it on exact ties)
+    const float gate = v > free_bits ? 1.f : (v == free_bits ? 0.5f : 0.f);
+    const float cl = gs * w_lhs * gate / rows, cr = gs * w_rhs * gate / rows;
+    for (int s = 0; s < S; ++s) {
+      float p[KPL], P[KPL], q[KPL], Q[KPL], usp, usq, dP[KPL], dQ[KPL], dl[KPL];
+      const long long base = (row * S + s) * K;
+      cat_probs<KPL>(lhs + base, K, lane, p, P, usp);
+      cat_probs<KPL>(rhs + base, K, lane, q, Q, usq);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        bool ok = lane + 32 * i < K;
+        dP[i] = ok ? cl * (logf(P[i]) - logf(Q[i]) + 1.0f) : 0.f;
+        dQ[i] = ok ? -cr * P[i] / Q[i] : 0.f;
+      }
+      cat_probs_bwd<KPL>(p, P, usp, dP, dl);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) if (lane + 32 * i < K) dlhs[base + lane + 32 * i] = dl[i];
+      cat_probs_bwd<KPL>(q, Q, usq, dQ, dl);
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) if (lane + 32 * i < K) drhs[base + lane + 32 * i] = dl[i];
+    }
+  }
+}
+
+// =================================================================================================
+// Two-hot symlog head   reference: TwoHotDist dreamer_utils.py:120-171 (255 buckets on linspace(-20,20))
+// =================================================================================================
+constexpr int NB = 255;
+__device__ __forceinline__ float bucket(int i) {
+  // torch.linspace(-20, 20, 255): start + i*step for the first half, end - (n-1-i)*step for the second (symmetric fill)
+  const float step = 40.0f / 254.0f;
+  return i < NB / 2 ? -20.0f + step * i : 20.0f - step * (NB - 1 - i);
+}
+__device__ __forceinline__ float symlogf_(float x) { return copysignf(logf(fabsf(x) + 1.0f), x) * (x != 0.f); }
+__device__ __forceinline__ float symexpf_(float y) { return copysignf(expf(fabsf(y)) - 1.0f, y) * (y != 0.f); }
+
+// mode 0: out[r] = log_prob(x[r]) ; mode 1: out[r] = mean
+__global__ void __launch_bounds__(THREADS) twohot_fwd_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, int mode,
+                                                             float* __restrict__ out, long long rows) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
+    const float* lg = logits + row * ldl;
+    float v[8], mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; v[i] = k < NB ? lg[k] : -INFINITY; mx = fmaxf(mx, v[i]); }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (lane + 32 * i < NB) ? expf(v[i] - mx) : 0.f;
+    s = warp_sum(s);
+    if (mode == 1) {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < NB) m += expf(v[i] - mx) / s * bucket(k); }
+      m = warp_sum(m);
+      if (lane == 0) out[row] = symexpf_(m);
+    } else {
+      const float lse = mx + logf(s);
+      const float xs = symlogf_(x[row]);
+      int cnt_le = 0, cnt_gt = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < NB) { cnt_le += bucket(k) <= xs; cnt_gt += bucket(k) > xs; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { cnt_le += __shfl_xor_sync(0xffffffffu, cnt_le, o); cnt_gt += __shfl_xor_sync(0xffffffffu, cnt_gt, o); }
+      int below = min(max(cnt_le - 1, 0), NB - 1), above = min(max(NB - cnt_gt, 0), NB - 1);
+      float wb, wa;
+      if (below == above) { wb = 0.5f; wa = 0.5f; }
+      else { float db = fabsf(bucket(below) - xs), da = fabsf(bucket(above) - xs); wb = da / (db + da); wa = db / (db + da); }
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int k = lane + 32 * i;
+        if (k < NB) { float t = (k == below ? wb : 0.f) + (k == above ? wa : 0.f); if (t != 0.f) acc += t * (v[i] - lse); }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[row] = acc;
+    }
+  }
+}
+
+// dlogits = dout[r] * d out / d logits
+__global__ void __launch_bounds__(THREADS) twohot_bwd_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, int mode,
+                                                             const float* __restrict__ dout, float scale, float* __restrict__ dlogits, long long lddl,
+                                                             long long rows) {
+  const int lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
+    const float* lg = logits + row * ldl;
+    float v[8], mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; v[i] = k < NB ? lg[k] : -INFINITY; mx = fmaxf(mx, v[i]); }
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = (lane + 32 * i < NB) ? expf(v[i] - mx) : 0.f; s += v[i]; }
+    s = warp_sum(s);
+    const float g = dout[row] * scale;
+    float* dl = dlogits + row * lddl;
+    if (mode == 1) {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < NB) m += v[i] / s * bucket(k); }
+      m = warp_sum(m);
+      const float gm = g * expf(fabsf(m));        // d symexp(y)/dy = exp(|y|)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < NB) dl[k] = gm * (v[i] / s) * (bucket(k) - m); }
+    } else {
+      const float xs = symlogf_(x[row]);
+      int cnt_le = 0, cnt_gt = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < NB) { cnt_le += bucket(k) <= xs; cnt_gt += bucket(k) > xs; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { cnt_le += __shfl_xor_sync(0xffffffffu, cnt_le, o); cnt_gt += __shfl_xor_sync(0xffffffffu, cnt_gt, o); }
+      int below = min(max(cnt_le - 1, 0), NB - 1), above = min(max(NB - cnt_gt, 0), NB - 1);
+      float wb, wa;
+      if (below == above) { wb = 0.5f; wa = 0.5f; }
+      else { float db = fabsf(bucket(below) - xs), da = fabsf(bucket(above) - xs); wb = da / (db + da); wa = db / (db + da); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int k = lane + 32 * i;
+        if (k < NB) { float t = (k == below ? wb : 0.f) + (k == above ? wa : 0.f); dl[k] = g * (t - v[i] / s); }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// Normal actor head   reference: DistLayer 'normal' dreamer_utils.py:814-819; Independent(Normal).entropy
+//   out[r, 0:A] -> mean = tanh ; out[r, A:2A] -> std = 0.9*sigmoid(.+2)+0.1 ; action = mean + std*eps
+// =================================================================================================
+template <typename T>
+__global__ void actor_head_fwd_kernel(const float* __restrict__ out, long long ldo, const float* __restrict__ eps, int use_mean,
+                                      float* __restrict__ action, long long lda, T* __restrict__ action_t, long long ldat,
+                                      float* __restrict__ ent, long long rows, int A) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  float e = 0.f;
+  for (int a = 0; a < A; ++a) {
+    float mean = tanhf(out[i * ldo + a]);
+    float std = 0.9f * sigmoidf_(out[i * ldo + A + a] + 2.0f) + 0.1f;
+    float act = use_mean ? mean : mean + std * eps[i * A + a];
+    if (action) action[i * lda + a] = act;
+    if (action_t) action_t[i * ldat + a] = from_f32<T>(act);
+    e += 0.5f + 0.9189385332046727f + logf(std);
+  }
+  if (ent) ent[i] = e;
+}
+
+template <typename T>
+__global__ void actor_head_bwd_kernel(const float* __restrict__ out, long long ldo, const float* __restrict__ eps, const T* __restrict__ daction,
+                                      long long ldda, const float* __restrict__ dent, float dent_scale, float* __restrict__ dout, long long lddo,
+                                      long long rows, int A) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float de = dent ? dent[i] * dent_scale : dent_scale;
+  for (int a = 0; a < A; ++a) {
+    float mean = tanhf(out[i * ldo + a]);
+    float sg = sigmoidf_(out[i * ldo + A + a] + 2.0f);
+    float std = 0.9f * sg + 0.1f;
+    float da = daction ? to_f32(daction[i * ldda + a]) : 0.f;
+    float dstd = da * eps[i * A + a] + de / std;
+    dout[i * lddo + a] = da * (1.0f - mean * mean);
+    dout[i * lddo + A + a] = dstd * 0.9f * sg * (1.0f - sg);
+  }
+}
+
+// =================================================================================================
+// lambda-return   reference: lambda_return dreamer_utils.py:228-253 (reverse scan), ActorCritic.target dreamer.py:440-453
+//   R_t = r_t + g*((1-l)*v_{t+1} + l*R_{t+1}),  R_H = v_H.   reward, value: [H+1, N]; target: [H, N]
+// =================================================================================================
+__global__ void lambda_return_fwd_kernel(const float* __restrict__ reward, const float* __restrict__ value, float gamma, float lambda,
+                                         float* __restrict__ target, int H, long long N) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float last = value[(long long)H * N + n];
+  for (int t = H - 1; t >= 0; --t) {
+    float inp = reward[t * N + n] + gamma * value[(long long)(t + 1) * N + n] * (1.0f - lambda);
+    last = inp + gamma * lambda * last;
+    target[t * N + n] = last;
+  }
+}
+
+// dtarget given as coef[t] (same for every n: the actor objective is a plain mean) or per-element array
+__global__ void lambda_return_bwd_kernel(const float* __restrict__ dtarget, const float* __restrict__ dt_scale, float gamma, float lambda,
+                                         float* __restrict__ dreward, float* __restrict__ dvalue, int H, long long N) {
+  long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float sc = dt_scale ? *dt_scale : 1.0f;
+  float acc = 0.f;
+  dvalue[n] = 0.f;
+  for (int t = 0; t < H; ++t) {
+    acc = dtarget[t * N + n] * sc + gamma * lambda * acc;
+    dreward[t * N + n] = acc;
+    float dv = gamma * (1.0f - lambda) * acc;
+    if (t == H - 1) dv += gamma * lambda * acc;
+    dvalue[(long long)(t + 1) * N + n] = dv;
+  }
+  dreward[(long long)H * N + n] = 0.f;
+}
+
+// =================================================================================================
+// MSE image likelihood   reference: MSEDist.log_prob dreamer_utils.py:74-83 on (obs/255 - 0.5) dreamer.py:294-295
+//   like[r] = -sum_{chw} (mean - (u8/255 - 0.5))^2 ;  dmean = -2 (mean - x) * dlike[r] * scale
+// =================================================================================================
+__global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ mean, const uint8_t* __restrict__ obs, float* __restrict__ like, int E) {
+  const long long r = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < E; i += 256) {
+    float x = (float)obs[r * E + i] / 255.0f - 0.5f;
+    float d = mean[r * E + i] - x;
+    s += d * d;
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; like[r] = -t; }
+}
+__global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ mean, const uint8_t* __restrict__ obs, const float* __restrict__ dlike,
+                                                      const float* __restrict__ gscale, float scale, float* __restrict__ dmean, int E) {
+  const long long r = blockIdx.x;
+  const float g = (dlike ? dlike[r] : 1.0f) * scale * (gscale ? *gscale : 1.0f);
+  for (int i = threadIdx.x; i < E; i += 256) {
+    float x = (float)obs[r * E + i] / 255.0f - 0.5f;
+    dmean[r * E + i] = -2.0f * (mean[r * E + i] - x) * g;
+  }
+}
+
+// =================================================================================================
+// small utilities
+// =================================================================================================
+// out[0] = mean, out[1] = unbiased std (torch .std()), single block
+__global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  __shared__ float s_mean;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 32; ++i) t += red[i]; s_mean = t / n; }
+  __syncthreads();
+  const float m = s_mean;
+  float v = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 1024) { float d = x[i] - m; v += d * d; }
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 32; ++i) t += red[i]; out[0] = m; out[1] = n > 1 ? sqrtf(t / (n - 1)) : 0.f; }
+}
+
+// y[i] = a * x[i] + b   with optional device-side scalars (a_dev / b_dev) -> used for normalisation by RewardEMA
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = from_f32<TO>(to_f32(x[i]));
+}
+
+// strided 2-D copy with cast: dst[r, c] = src[r, c]   (used to assemble [stoch | action] / [x | h] operand buffers)
+template <typename TI, typename TO>
+__global__ void copy2d_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, long long rows, int cols,
+                              const float* __restrict__ row_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  long long r = i / cols; int c = (int)(i % cols);
+  float v = to_f32(src[r * lds + c]);
+  if (row_scale) v *= row_scale[r];
+  dst[r * ldd + c] = from_f32<TO>(v);
+}
+
+// dst[r, 0:cols] (+)= scale[r] * src[idx[r], 0:cols]   (idx < 0 -> zeros).  Time shifts of the RSSM inputs
+// ("prev stoch" = posterior of t-1, masked by 1 - is_first: obs_step dreamer_utils.py:432-436) and their adjoints.
+template <typename TI, typename TO>
+__global__ void gather_rows_kernel(const TI* __restrict__ src, long long lds, const int* __restrict__ idx, const float* __restrict__ scale,
+                                   TO* __restrict__ dst, long long ldd, long long rows, int cols, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  long long r = i / cols; int c = (int)(i % cols);
+  long long sr = idx ? (long long)idx[r] : r;
+  float v = sr < 0 ? 0.f : to_f32(src[sr * lds + c]) * (scale ? scale[r] : 1.f);
+  TO* o = dst + r * ldd + c;
+  *o = from_f32<TO>(accumulate ? to_f32(*o) + v : v);
+}
+
+}  // namespace genrl
+
+using namespace genrl;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
+                                void* y, long long ldy, float* stats, long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  DISPATCH_T(dtype, (ln_act_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D)));
+  return check_launch("ln_act_fwd");
+}
+
+extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma, const float* beta,
+                                const float* stats, int act, void* dx, long long lddx, float* dgamma, float* dbeta, float* dlin_bias,
+                                long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  GENRL_REQUIRE(3 * D * 4 <= 200 * 1024, "ln_act_bwd: D too large");
+  size_t smem = (size_t)3 * D * sizeof(float);
+  DISPATCH_T(dtype, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ln_act_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx,
+                                                                              lddx, dgamma, dbeta, dlin_bias, M, D);
+  });
+  return check_launch("ln_act_bwd");
+}
+
+extern "C" int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  long long rpb = 256;
+  dim3 grid(ceil_div(D, 256), ceil_div(M, rpb));
+  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D, rpb)));
+  return check_launch("colsum");
+}
+
+extern "C" int genrl_gru_fwd(void* stream, const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
+                             float* hout, long long ldho, void* hout_t, long long ldht, float* stats, long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  DISPATCH_T(dtype, (gru_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D)));
+  return check_launch("gru_fwd");
+}
+
+extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, const void* z, long long ldz, const float* gamma, const float* beta,
+                             const float* hprev, long long ldh, const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp,
+                             float* dgamma, float* dbeta, long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  size_t smem = (size_t)6 * D * sizeof(float);
+  GENRL_REQUIRE(smem <= 200 * 1024, "gru_bwd: D too large");
+  DISPATCH_T(dtype, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(gru_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gru_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+                                                                           dhprev, lddhp, dgamma, dbeta, M, D);
+  });
+  return check_launch("gru_bwd");
+}
+
+extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset,
+                                    int sample, void* stoch, long long ld_stoch, float* stoch32, long long ld_stoch32, int* idx, long long rows,
+                                    int S, int K, int dtype) {
+  if (rows <= 0) return 0;
+  GENRL_REQUIRE(K <= 32 * KPL, "cat_sample: K=%d > %d unsupported", K, 32 * KPL);
+  DISPATCH_T(dtype, (cat_sample_fwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, noise, seed, offset, sample, (T*)stoch, ld_stoch,
+                                                                                                     stoch32, ld_stoch32, idx, rows, S, K)));
+  return check_launch("cat_sample_fwd");
+}
+
+extern "C" int genrl_cat_sample_bwd(void* stream, const float* logit, const void* dstoch, long long ld_ds, int sample, float* dlogit, int accumulate,
+                                    long long rows, int S, int K, int dtype) {
+  if (rows <= 0) return 0;
+  GENRL_REQUIRE(K <= 32 * KPL, "cat_sample: K=%d > %d unsupported", K, 32 * KPL);
+  DISPATCH_T(dtype, (cat_sample_bwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S, K)));
+  return check_launch("cat_sample_bwd");
+}
+
+extern "C" int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, float free_bits, float* value, float* out4, long long rows, int S, int K) {
+  if (rows <= 0) return 0;
+  GENRL_REQUIRE(K <= 32 * KPL, "kl: K=%d unsupported", K);
+  cudaMemsetAsync(out4, 0, 4 * sizeof(float), ST(stream));
+  kl_fwd_kernel<<<row_grid(rows, 148 * 4), THREADS, 0, ST(stream)>>>(lhs, rhs, free_bits, value, out4, rows, S, K);
+  return check_launch("kl_fwd");
+}
+
+extern "C" int genrl_kl_bwd(void* stream, const float* lhs, const float* rhs, const float* value, float free_bits, float w_lhs, float w_rhs,
+                            const float* gscale, float* dlhs, float* drhs, long long rows, int S, int K) {
+  if (rows <= 0) return 0;
+  kl_bwd_kernel<<<row_grid(rows, 148 * 8), THREADS, 0, ST(stream)>>>(lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows, S, K);
+  return check_launch("kl_bwd");
+}
+
+extern "C" int genrl_twohot_fwd(void* stream, const float* logits, long long ldl, const float* x, int mode, float* out, long long rows) {
+  if (rows <= 0) return 0;
+  twohot_fwd_kernel<<<row_grid(rows, 148 * 16), THREADS, 0, ST(stream)>>>(logits, ldl, x, mode, out, rows);
+  return check_launch("twohot_fwd");
+}
+
+extern "C" int genrl_twohot_bwd(void* stream, const float* logits, long long ldl, const float* x, int mode, const float* dout, float scale,
+                                float* dlogits, long long lddl, long long rows) {
+  if (rows <= 0) return 0;
+  twohot_bwd_kernel<<<row_grid(rows, 148 * 16), THREADS, 0, ST(stream)>>>(logits, ldl, x, mode, dout, scale, dlogits, lddl, rows);
+  return check_launch("twohot_bwd");
+}
+
+extern "C" int genrl_actor_head_fwd(void* stream, const float* out, long long ldo, const float* eps, int use_mean, float* action, long long lda,
+                                    void* action_t, long long ldat, float* ent, long long rows, int A, int dtype) {
+  if (rows <= 0) return 0;
+  DISPATCH_T(dtype, (actor_head_fwd_kernel<T><<<ceil_div(rows, 128), 128, 0, ST(stream)>>>(out, ldo, eps, use_mean, action, lda, (T*)action_t, ldat, ent, rows, A)));
+  return check_launch("actor_head_fwd");
+}
+
+extern "C" int genrl_actor_head_bwd(void* stream, const float* out, long long ldo, const float* eps, const void* daction, long long ldda,
+                                    const float* dent, float dent_scale, float* dout, long long lddo, long long rows, int A, int dtype) {
+  if (rows <= 0) return 0;
+  DISPATCH_T(dtype, (actor_head_bwd_kernel<T><<<ceil_div(rows, 128), 128, 0, ST(stream)>>>(out, ldo, eps, (const T*)daction, ldda, dent, dent_scale, dout, lddo, rows, A)));
+  return check_launch("actor_head_bwd");
+}
+
+extern "C" int genrl_lambda_return_fwd(void* stream, const float* reward, const float* value, float gamma, float lambda, float* target, int H, long long N) {
+  if (N <= 0) return 0;
+  lambda_return_fwd_kernel<<<ceil_div(N, 128), 128, 0, ST(stream)>>>(reward, value, gamma, lambda, target, H, N);
+  return check_launch("lambda_return_fwd");
+}
+
+extern "C" int genrl_lambda_return_bwd(void* stream, const float* dtarget, const float* dt_scale, float gamma, float lambda, float* dreward,
+                                       float* dvalue, int H, long long N) {
+  if (N <= 0) return 0;
+  lambda_return_bwd_kernel<<<ceil_div(N, 128), 128, 0, ST(stream)>>>(dtarget, dt_scale, gamma, lambda, dreward, dvalue, H, N);
+  return check_launch("lambda_return_bwd");
+}
+
+extern "C" int genrl_mse_fwd(void* stream, const float* mean, const unsigned char* obs, float* like, long long rows, int E) {
+  if (rows <= 0) return 0;
+  mse_fwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(mean, obs, like, E);
+  return check_launch("mse_fwd");
+}
+
+extern "C" int genrl_mse_bwd(void* stream, const float* mean, const unsigned char* obs, const float* dlike, const float* gscale, float scale,
+                             float* dmean, long long rows, int E) {
+  if (rows <= 0) return 0;
+  mse_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(mean, obs, dlike, gscale, scale, dmean, E);
+  return check_launch("mse_bwd");
+}
+
+extern "C" int genrl_mean_std(void* stream, const float* x, long long n, float* out2) {
+  mean_std_kernel<<<1, 1024, 0, ST(stream)>>>(x, n, out2);
+  return check_launch("mean_std");
+}
+
+// dst[r, 0:cols] = cast(src[r, 0:cols]) * row_scale[r]      dtypes: GENRL_F32 / GENRL_BF16 each side
+extern "C" int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
+                            int cols, const float* row_scale) {
+  if (rows <= 0 || cols <= 0) return 0;
+  unsigned grid = (unsigned)ceil_div(rows * cols, 256);
+  cudaStream_t st = ST(stream);
+  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) copy2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, row_scale);
+  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) copy2d_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols, row_scale);
+  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) copy2d_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols, row_scale);
+  else copy2d_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols, row_scale);
+  return check_launch("copy2d");
+}
+
+extern "C" int genrl_gather_rows(void* stream, const void* src, long long lds, int src_dtype, const int* idx, const float* scale, void* dst,
+                                 long long ldd, int dst_dtype, long long rows, int cols, int accumulate) {
+  if (rows <= 0 || cols <= 0) return 0;
+  unsigned grid = (unsigned)ceil_div(rows * cols, 256);
+  cudaStream_t st = ST(stream);
+  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) gather_rows_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, idx, scale, (float*)dst, ldd, rows, cols, accumulate);
+  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) gather_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, lds, idx, scale, (__nv_bfloat16*)dst, ldd, rows, cols, accumulate);
+  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) gather_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, idx, scale, (float*)dst, ldd, rows, cols, accumulate);
+  else gather_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, idx, scale, (__nv_bfloat16*)dst, ldd, rows, cols, accumulate);
+  return check_launch("gather_rows");
+}

@@ -1,0 +1,502 @@
+// GEMM for the GenRL hot path on sm_100a.
+//
+//   C[M,N] (+)= op(A)[M,K] * op(W)[N,K]^T + bias[N]
+//
+// * bf16 operands -> tcgen05.mma (UMMA 128xBNx16, fp32 accumulators in TMEM), operands staged by TMA
+//   (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring; warp-specialised:
+//   warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (tcgen05.ld).
+//   Both K-major and MN-major operands are supported (transA / transW) so forward, dgrad and wgrad
+//   of every Linear / lowered conv in the path run on the same kernel without transposed copies.
+// * fp32 operands -> register-tiled SIMT kernel (the fp32 parity mode; 1e-4 parity needs full fp32).
+//
+// Replaces: every nn.Linear / nn.Conv2d / nn.ConvTranspose2d call of reference agent/dreamer_utils.py
+// (e.g. :339-346 RSSM projections, :760 GRU layer, :733-735 MLP dense layers, :586,:668 conv stacks).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace genrl {
+
+// =================================================================================================
+// PTX wrappers
+// =================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (SM100 format, cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// =================================================================================================
+// tcgen05 GEMM kernel
+// =================================================================================================
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int M, N, K;
+  int ldc;
+  int c_dtype;          // GENRL_F32 / GENRL_BF16
+  int accumulate;       // C += result (fp32 C only)
+  int atomic;           // use atomicAdd (split-K)
+  int kb_per_split;     // k-blocks handled per blockIdx.z
+  int num_kb;
+  const float* bias;
+  void* C;
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM;
+  const int n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;   // host guarantees >= 1
+
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+        const int k0 = kb * TC_BK;
+        if (!A_MN) {
+          tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                       // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 64; ++j)                                    // box {64 m, 64 k}
+            tma_load_2d(&tmA, &full_bar[stage], sa + j * (64 * TC_BK * 2), m0 + 64 * j, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);                       // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)                                       // box {64 n, 64 k}
+            tma_load_2d(&tmB, &full_bar[stage], sb + j * (64 * TC_BK * 2), n0 + 64 * j, k0);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      // instruction descriptor (cute InstrDescriptor): c=F32, a=b=BF16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // K-major SW128: rows 128B apart, 8-row groups 1024B apart (SBO); +32B per K=16 step.
+          // MN-major SW128: 64-element MN chunks 8192B apart (LBO), 8-k-row groups 1024B apart (SBO); +2048B per K=16.
+          const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 64 * TC_BK * 2, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 64 * TC_BK * 2, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);           // frees the smem slot once the MMAs have read it
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= p.N) break;                  // warp-uniform
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+      if (!row_ok) continue;
+      const int col0 = n0 + c;
+      const int ncols = min(32, p.N - col0);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (add_bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(p.bias + col0 + j);
+      }
+      if (p.c_dtype == GENRL_F32) {
+        float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+        if (p.atomic) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(out + j, f[j]);
+        } else {
+          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (p.accumulate) {
+                float4 prev = *reinterpret_cast<float4*>(out + j);
+                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+              }
+              *reinterpret_cast<float4*>(out + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = p.accumulate ? out[j] + f[j] : f[j];
+          }
+        }
+      } else {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+        const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+            __nv_bfloat162 a1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+            __nv_bfloat162 a3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+            pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+            *reinterpret_cast<uint4*>(out + j) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// =================================================================================================
+// fp32 SIMT GEMM (parity mode): generic strides, 64x64x16 tiles, 4x4 outputs per thread
+// =================================================================================================
+struct SimtParams {
+  int M, N, K;
+  const float* A; long long sam, sak;     // A(m,k) = A[m*sam + k*sak]
+  const float* W; long long swn, swk;     // W(n,k) = W[n*swn + k*swk]
+  float* C; int ldc;
+  const float* bias;
+  int accumulate;
+};
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loader mapping: pick the contiguous direction to be the fast thread index
+  const bool a_kfast = (p.sak == 1);
+  const bool w_kfast = (p.swk == 1);
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int e = tid + it * 256;                 // 1024 elements per tile
+      int mm, kk;
+      if (a_kfast) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < p.M && gk < p.K) ? p.A[gm * p.sam + gk * p.sak] : 0.f;
+      int nn, k2;
+      if (w_kfast) { k2 = e & 15; nn = e >> 4; } else { nn = e & 63; k2 = e >> 6; }
+      int gn = n0 + nn; gk = k0 + k2;
+      Ws[k2][nn] = (gn < p.N && gk < p.K) ? p.W[gn * p.swn + gk * p.swk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m0 + ty * 4 + i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= p.N) continue;
+      float v = acc[i][j] + (p.bias ? p.bias[gn] : 0.f);
+      float* o = p.C + (size_t)gm * p.ldc + gn;
+      *o = p.accumulate ? *o + v : v;
+    }
+  }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// rows x cols bf16 matrix, row-major with leading dimension ld (elements); box = {box_cols, box_rows}
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  GENRL_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GENRL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows, cols, ld, base);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams p, int splits, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
+  constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    GENRL_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_tc) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM), splits);
+  kern<<<grid, TC_THREADS, SMEM, st>>>(ta, tb, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, TcParams p, int splits, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_tc<64, A_MN, B_MN>(ta, tb, p, splits, st);
+    case 128: return launch_tc<128, A_MN, B_MN>(ta, tb, p, splits, st);
+    case 192: return launch_tc<192, A_MN, B_MN>(ta, tb, p, splits, st);
+    default: return launch_tc<256, A_MN, B_MN>(ta, tb, p, splits, st);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// choose BN and split-K to minimise (waves x tile cost) on the SM count
+static void choose_tiling(int M, int N, int K, bool allow_split, int* bn_out, int* splits_out) {
+  const int sms = num_sms();
+  const int cands[4] = {64, 128, 192, 256};
+  const int mt = ceil_div(M, TC_BM);
+  const int num_kb = ceil_div(K, TC_BK);
+  double best = 1e30;
+  int best_bn = 128, best_s = 1;
+  for (int ci = 0; ci < 4; ++ci) {
+    int bn = cands[ci];
+    if (bn > 64 && bn - 64 >= N) continue;              // needlessly wide
+    int nt = ceil_div(N, bn);
+    int max_s = allow_split ? 16 : 1;
+    for (int s = 1; s <= max_s; s *= 2) {
+      if (s > num_kb) break;
+      long long tiles = (long long)mt * nt * s;
+      long long waves = (tiles + sms - 1) / sms;
+      int kb = ceil_div(num_kb, s);
+      // per-tile cost ~ k-blocks * (MMA cycles ~ bn) + fixed overhead; epilogue ~ bn; atomics penalty for splits
+      double cost = (double)waves * ((double)kb * (bn + 32.0 * (bn <= 64)) + 6.0 * bn + 400.0) * (s > 1 ? 1.05 : 1.0);
+      if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+    }
+  }
+  *bn_out = best_bn;
+  *splits_out = best_s;
+}
+
+}  // namespace genrl
+
+using namespace genrl;
+
+// C-ABI -------------------------------------------------------------------------------------------
+// C[M,N] (+)= op(A) * op(W)^T + bias.  A: [M,K] row-major (lda) or, if transA, [K,M] row-major (lda).
+// W: [N,K] row-major (ldw) or, if transW, [K,N] row-major (ldw).  in_dtype: GENRL_F32 (SIMT) or
+// GENRL_BF16 (tcgen05).  C: [M,N] row-major (ldc) of c_dtype; accumulate requires fp32 C.
+extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W,
+                          long long ldw, int transW, int in_dtype, void* C, long long ldc, int c_dtype, const float* bias,
+                          int accumulate) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0) return 0;
+  GENRL_REQUIRE(K > 0, "genrl_gemm: K must be positive");
+  if (in_dtype == GENRL_F32) {
+    GENRL_REQUIRE(c_dtype == GENRL_F32, "genrl_gemm: fp32 operands need fp32 output");
+    SimtParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.A = reinterpret_cast<const float*>(A);
+    p.sam = transA ? 1 : lda; p.sak = transA ? lda : 1;
+    p.W = reinterpret_cast<const float*>(W);
+    p.swn = transW ? 1 : ldw; p.swk = transW ? ldw : 1;
+    p.C = reinterpret_cast<float*>(C); p.ldc = (int)ldc; p.bias = bias; p.accumulate = accumulate;
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+    return check_launch("gemm_simt_kernel");
+  }
+  GENRL_REQUIRE(in_dtype == GENRL_BF16, "genrl_gemm: unknown operand dtype %d", in_dtype);
+  GENRL_REQUIRE(!(accumulate && c_dtype != GENRL_F32), "genrl_gemm: accumulate needs fp32 C");
+  GENRL_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "genrl_gemm: bf16 leading dimensions must be multiples of 8 (lda=%lld ldw=%lld)", lda, ldw);
+  GENRL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "genrl_gemm: operands must be 16B aligned");
+  int bn, splits;
+  choose_tiling(M, N, K, accumulate != 0 && c_dtype == GENRL_F32, &bn, &splits);
+  CUtensorMap ta, tb;
+  if (!transA) { if (make_map(&ta, A, M, K, lda, 64, TC_BM)) return 1; }
+  else         { if (make_map(&ta, A, K, M, lda, 64, 64)) return 1; }
+  if (!transW) { if (make_map(&tb, W, N, K, ldw, 64, bn)) return 1; }
+  else         { if (make_map(&tb, W, K, N, ldw, 64, 64)) return 1; }
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.c_dtype = c_dtype; p.accumulate = accumulate;
+  p.atomic = splits > 1;
+  p.num_kb = ceil_div(K, TC_BK);
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.bias = bias; p.C = C;
+  if (!transA && !transW) return dispatch_bn<false, false>(bn, ta, tb, p, splits, st);
+  if (!transA && transW) return dispatch_bn<false, true>(bn, ta, tb, p, splits, st);
+  if (transA && !transW) return dispatch_bn<true, false>(bn, ta, tb, p, splits, st);
+  return dispatch_bn<true, true>(bn, ta, tb, p, splits, st);
+}

@@ -1,0 +1,122 @@
+/* genrl_b200 — C-ABI of the B200-native GenRL/Dreamer world-model training hot path.
+ *
+ * The reference (mazpie/genrl) has no FFI layer: its "kernels" are PyTorch library calls made from
+ * agent/dreamer_utils.py, agent/dreamer.py and agent/video_utils.py.  Each entry point below replaces the group of
+ * torch calls cited beside it.  Conventions:
+ *   - every function returns 0 on success; on failure the message is in genrl_last_error();
+ *   - `stream` is a cudaStream_t passed as void* (the host passes torch.cuda.current_stream().cuda_stream);
+ *   - all pointers are DEVICE pointers owned by the caller; no function allocates or synchronises;
+ *   - dtype codes: 0 = fp32, 1 = bf16 (activation storage type; statistics, logits, losses and gradients of
+ *     parameters are always fp32);
+ *   - matrices are row-major with an explicit leading dimension (`ld*`, in elements).
+ * The ctypes binding (genrl_b200/_lib.py) is generated from this file, so it is the single source of truth.
+ */
+#ifndef GENRL_B200_H
+#define GENRL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* genrl_last_error();
+int genrl_abi_version();
+int genrl_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* smem_optin);
+
+/* C[M,N] (+)= op(A) op(W)^T + bias.  Replaces nn.Linear / lowered nn.Conv2d / nn.ConvTranspose2d forward, dgrad and
+ * wgrad (dreamer_utils.py:339-346, :733-735, :760, :586, :668).  in_dtype 1 -> tcgen05 + TMA kernel, 0 -> fp32 SIMT. */
+int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W, long long ldw, int transW,
+               int in_dtype, void* C, long long ldc, int c_dtype, const float* bias, int accumulate);
+
+/* LayerNorm(+SiLU) rows: NormLayer dreamer_utils.py:844-859 / ImgChLayerNorm :1031-1040 + act (:744, :589). */
+int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act, void* y,
+                     long long ldy, float* stats, long long M, int D, int dtype);
+int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma, const float* beta,
+                     const float* stats, int act, void* dx, long long lddx, float* dgamma, float* dbeta, float* dlin_bias, long long M,
+                     int D, int dtype);
+int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype);
+
+/* GRUCell tail (LayerNorm(3D) + gates): dreamer_utils.py:777-785. */
+int genrl_gru_fwd(void* stream, const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
+                  float* hout, long long ldho, void* hout_t, long long ldht, float* stats, long long M, int D, int dtype);
+int genrl_gru_bwd(void* stream, const float* dh, long long lddh, const void* z, long long ldz, const float* gamma, const float* beta,
+                  const float* hprev, long long ldh, const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp,
+                  float* dgamma, float* dbeta, long long M, int D, int dtype);
+
+/* OneHotDist sample / mode with straight-through gradient: dreamer_utils.py:177-197, :410-416.
+ * noise != NULL: q ~ Exp(1) supplied by the caller (parity mode); else Philox(seed, offset). */
+int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset, int sample,
+                         void* stoch, long long ld_stoch, float* stoch32, long long ld_stoch32, int* idx, long long rows, int S, int K,
+                         int dtype);
+int genrl_cat_sample_bwd(void* stream, const float* logit, const void* dstoch, long long ld_ds, int sample, float* dlogit, int accumulate,
+                         long long rows, int S, int K, int dtype);
+
+/* EnsembleRSSM.kl_loss + entropies: dreamer_utils.py:534-555, dreamer.py:249-250.  out4 = {loss, mean value, ent lhs, ent rhs}. */
+int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, float free_bits, float* value, float* out4, long long rows, int S, int K);
+int genrl_kl_bwd(void* stream, const float* lhs, const float* rhs, const float* value, float free_bits, float w_lhs, float w_rhs,
+                 const float* gscale, float* dlhs, float* drhs, long long rows, int S, int K);
+
+/* TwoHotDist.log_prob (mode 0) / .mean (mode 1): dreamer_utils.py:120-171. */
+int genrl_twohot_fwd(void* stream, const float* logits, long long ldl, const float* x, int mode, float* out, long long rows);
+int genrl_twohot_bwd(void* stream, const float* logits, long long ldl, const float* x, int mode, const float* dout, float scale,
+                     float* dlogits, long long lddl, long long rows);
+
+/* DistLayer 'normal' head + rsample + entropy: dreamer_utils.py:814-819. */
+int genrl_actor_head_fwd(void* stream, const float* out, long long ldo, const float* eps, int use_mean, float* action, long long lda,
+                         void* action_t, long long ldat, float* ent, long long rows, int A, int dtype);
+int genrl_actor_head_bwd(void* stream, const float* out, long long ldo, const float* eps, const void* daction, long long ldda,
+                         const float* dent, float dent_scale, float* dout, long long lddo, long long rows, int A, int dtype);
+
+/* lambda_return reverse scan: dreamer_utils.py:228-253. */
+int genrl_lambda_return_fwd(void* stream, const float* reward, const float* value, float gamma, float lambda, float* target, int H,
+                            long long N);
+int genrl_lambda_return_bwd(void* stream, const float* dtarget, const float* dt_scale, float gamma, float lambda, float* dreward,
+                            float* dvalue, int H, long long N);
+
+/* MSEDist.log_prob against uint8 observations with the /255-0.5 preprocessing fused: dreamer_utils.py:74-83, dreamer.py:294-295. */
+int genrl_mse_fwd(void* stream, const float* mean, const unsigned char* obs, float* like, long long rows, int E);
+int genrl_mse_bwd(void* stream, const float* mean, const unsigned char* obs, const float* dlike, const float* gscale, float scale,
+                  float* dmean, long long rows, int E);
+
+int genrl_mean_std(void* stream, const float* x, long long n, float* out2);
+int genrl_mean_scale(void* stream, const float* x, long long n, float scale, float* out, int accumulate);
+int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
+                 int cols, const float* row_scale);
+
+/* dst[r,:] (+)= scale[r] * src[idx[r],:] (idx<0 -> 0): time shift + is_first masking of obs_step (dreamer_utils.py:432-436). */
+int genrl_gather_rows(void* stream, const void* src, long long lds, int src_dtype, const int* idx, const float* scale, void* dst,
+                      long long ldd, int dst_dtype, long long rows, int cols, int accumulate);
+
+/* Conv lowering: Encoder dreamer_utils.py:580-621, Decoder :656-706.  x_dtype -1 = uint8 NCHW with preprocessing fused. */
+int genrl_im2col(void* stream, const void* x, int x_dtype, void* col, long long ldcol, int col_dtype, int N, int H, int W, int C, int k,
+                 int Ho, int Wo);
+int genrl_col2im(void* stream, const void* col, long long ldcol, int col_dtype, const float* bias, void* y, int y_dtype, int nchw_out, int N,
+                 int Hi, int Wi, int C, int k, int Ho, int Wo);
+int genrl_nchw_to_nhwc(void* stream, const float* x, void* y, int y_dtype, int N, int C, int H, int W);
+int genrl_permute_abp(void* stream, const void* src, int src_dtype, void* dst, int dst_dtype, long long A, int B, int P, int accumulate);
+
+/* Optimizer.__call__: dreamer_utils.py:892-932 (clip -> weight decay -> Adam) on flat fp32 buffers. */
+int genrl_grad_sumsq(void* stream, const float* g, long long n, float* sumsq_out, int zero_first);
+int genrl_scale(void* stream, float* p, long long n, float s);
+int genrl_adam_step(void* stream, float* p, float* g, float* m, float* v, long long n, float lr, float eps, float clip, const float* sumsq,
+                    float* state, int finish);
+int genrl_pack_weights(void* stream, const void* table, int n_entries, int dst_dtype);
+int genrl_pack_entry_size();
+
+/* RewardEMA + actor objective: dreamer_utils.py:1014-1029, dreamer.py:392-429. */
+int genrl_quantile_ema(void* stream, const float* x, long long n, float q_lo, float q_hi, float alpha, float* ema, float* out4);
+int genrl_actor_objective(void* stream, const float* target, const float* ent, const float* offscale, float ent_scale, int H, long long N,
+                          float* out4, float* dcoef);
+
+/* Persistent time-loop of EnsembleRSSM.observe / VideoSSM.update: dreamer_utils.py:362-371 + :432-473 + :771-785. */
+long long genrl_rssm_scan_workspace_bytes(int B, int T, int D);
+int genrl_rssm_scan_fwd(void* stream, int B, int T, int D, const float* gx, const float* Wh, long long ldw, const float* gamma,
+                        const float* beta, const float* mask, const float* h0, float* deter, void* deter_t, long long ld_dt, void* hprev_t,
+                        long long ld_hp, int t_dtype, float* z, float* stats, void* workspace);
+int genrl_rssm_scan_bwd(void* stream, int B, int T, int D, const float* dh_ext, const float* z, const float* stats, const float* Wh,
+                        long long ldw, const float* gamma, const float* beta, const float* mask, const float* deter, const float* h0,
+                        void* dz_t, long long ld_dz, int t_dtype, float* dh0, float* dgamma, float* dbeta, void* workspace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

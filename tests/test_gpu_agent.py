@@ -1,0 +1,118 @@
+"""GPU parity of the drop-in agent API (GenRLAgent / DreamerAgent mirrors) against the reference's golden vectors.
+
+The fixtures (tests/golden/*.npz) hold the UNMODIFIED reference's outputs, metrics, gradients and parameters for two
+consecutive `update_wm` + `update_acting_behavior` calls; the CUDA path is fed the reference's own random draws
+(TapeNoise) so categorical sample indices must come out bit-exact and losses within 1e-4 (fp32 mode).
+"""
+import copy
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from genrl_b200.config import genrl_config, make_specs
+from tests.golden_utils import load_case
+
+DEV = "cuda:0"
+
+
+def build_agent(case, precision=32):
+    from genrl_b200.agent.genrl import GenRLAgent
+    from genrl_b200.agent.dreamer import DreamerAgent
+    g, meta, _ = load_case(case)
+    cfg = genrl_config(device=DEV, precision=precision, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"],
+                       agent=meta["kind"], **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    torch.manual_seed(1)
+    cls = GenRLAgent if meta["kind"] == "genrl" else DreamerAgent
+    agent = cls(name=meta["kind"], cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    missing = agent.load_state_dict({k: v for k, v in g["init"].items()}, strict=True)
+    data = {k: v.to(DEV) for k, v in g["data"].items()}
+    return agent, data, g, meta
+
+
+def relclose(a, b, rtol, atol, msg):
+    a = torch.as_tensor(a).detach().float().cpu(); b = torch.as_tensor(b).detach().float().cpu()
+    scale = float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= atol + rtol * scale, f"{msg}: max abs err {err:.3e} (scale {scale:.3e})"
+
+
+@pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer"])
+def test_agent_update_matches_reference_golden_fp32(case):
+    from genrl_b200 import ops
+    agent, data, g, meta = build_agent(case, 32)
+    # same initial weights as the reference from the seed alone (module creation order mirrors the reference)
+    ops.set_noise(ops.TapeNoise(g["tape"], DEV))
+    flips = 0
+    for step in range(2):
+        state, outputs, metrics = agent.update_wm(data, step)
+        start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+        ref = g[f"ref{step}"]
+        for grp in ("post", "prior"):
+            mine = outputs[grp]["stoch"].float().cpu()
+            flips += int((mine != ref[f"outputs/{grp}/stoch"]).any(-1).sum())
+            for k in ("deter", "logit"):
+                relclose(outputs[grp][k], ref[f"outputs/{grp}/{k}"], 1e-4, 2e-5, f"step {step} {grp}.{k}")
+        assert flips == 0, f"{flips} categorical sample indices differ from the reference"
+        relclose(outputs["embed"], ref["outputs/embed"], 1e-4, 2e-5, "embed")
+        relclose(outputs["feat"], ref["outputs/feat"], 1e-4, 2e-5, "feat")
+        relclose(outputs["kl"], ref["outputs/kl"], 1e-4, 2e-5, "kl value")
+        for k in ("observation", "reward"):
+            relclose(outputs["likes"][k], ref[f"outputs/likes/{k}"], 1e-4, 1e-4, f"likes.{k}")
+        for k, v in meta["metrics"][step].items():
+            assert k in metrics, f"metric {k} missing"
+            mv = float(torch.as_tensor(metrics[k]).float().cpu().reshape(-1)[0])
+            tol = 2e-3 if k.endswith("grad_norm") else 2e-4
+            assert abs(mv - v) <= tol * max(1.0, abs(v)) + 1e-5, f"step {step} metric {k}: {mv} vs reference {v}"
+    assert ops.noise.pos == len(ops.noise.items), "every reference draw must be consumed"
+    sd = agent.state_dict()
+    worst = 0.0
+    for k, v in g["ref1"].items():
+        if not k.startswith("params/"):
+            continue
+        name = k[len("params/"):]
+        err = float((sd[name].float().cpu() - v).abs().max())
+        worst = max(worst, err)
+        assert err <= 5e-6 + 1e-4 * float(v.abs().max()), f"parameter {name} after 2 updates: err {err:.3e}"
+    ops.set_noise(ops.PhiloxNoise(0))
+
+
+def test_agent_bf16_mode_runs_and_tracks_fp32():
+    from genrl_b200 import ops
+    agent, data, g, meta = build_agent("tiny_genrl", 16)
+    ops.set_noise(ops.TapeNoise(g["tape"], DEV))
+    state, outputs, metrics = agent.update_wm(data, 0)
+    ref = meta["metrics"][0]
+    for k in ("kl_loss", "observation_loss", "reward_loss", "model_loss"):
+        mv = float(metrics[k])
+        assert abs(mv - ref[k]) <= 2e-2 * max(1.0, abs(ref[k])), f"bf16 {k}: {mv} vs {ref[k]}"
+    ops.set_noise(ops.PhiloxNoise(0))
+    start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+    for k, v in metrics.items():
+        assert np.isfinite(float(torch.as_tensor(v).float().cpu().reshape(-1)[0])), k
+
+
+def test_agent_fast_noise_pickle_and_act():
+    from genrl_b200 import ops
+    agent, data, g, meta = build_agent("tiny_genrl", 32)
+    ops.set_noise(ops.PhiloxNoise(123))
+    state, metrics = agent.update(data, 0)
+    assert all(np.isfinite(float(torch.as_tensor(v).float().cpu().reshape(-1)[0])) for v in metrics.values())
+    buf = io.BytesIO()
+    torch.save({"agent": agent}, buf)                       # train.py:387-398 pickles the whole agent
+    buf.seek(0)
+    agent2 = torch.load(buf, weights_only=False)["agent"]
+    for (k, a), (_, b) in zip(agent.state_dict().items(), agent2.state_dict().items()):
+        assert torch.equal(a, b), k
+    state2, metrics2 = agent2.update(data, 1)
+    assert np.isfinite(float(metrics2["model_loss"]))
+    obs = {"observation": np.zeros((3, 64, 64), np.uint8), "reward": np.zeros((), np.float32), "is_first": np.array(True),
+           "is_last": np.array(False), "is_terminal": np.array(False), "discount": np.ones((), np.float32)}
+    action, st = agent2.act(obs, None, 0, eval_mode=False, state=None)
+    assert action.shape == (meta["A"],) and np.all(np.abs(action) <= 2.0)
+    action, st = agent2.act(obs, None, 1, eval_mode=True, state=st)
+    assert action.shape == (meta["A"],)
