@@ -54,6 +54,7 @@ class _Lib:
         self._dll = None
         self.protos = parse_header()
         self.launches = 0          # number of kernel-launching C-ABI calls made (bench.py reports it)
+        self.profile = None        # when a list: (name, start_event, end_event, args) per call (bench.py roofline pass)
 
     def load(self):
         if self._dll is not None:
@@ -80,6 +81,16 @@ class _Lib:
 
             def call(*args, _fn=fn, _name=name):
                 self.launches += 1
+                if self.profile is not None:
+                    import torch
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    rc = _fn(*args)
+                    e1.record()
+                    self.profile.append((_name, e0, e1, args[1:4], args))
+                    if rc != 0:
+                        raise GenrlError(f"{_name} failed: {self._dll.genrl_last_error().decode()}")
+                    return rc
                 rc = _fn(*args)
                 if rc != 0:
                     raise GenrlError(f"{_name} failed: {self._dll.genrl_last_error().decode()}")

@@ -5,6 +5,8 @@
 // and the adjoints swap roles (conv dgrad = col2im, convT dgrad = im2col).  The uint8 NCHW -> (x/255 - 0.5)
 // preprocessing (dreamer.py:294-295) is fused into the first im2col.
 #include "common.cuh"
+#include "rowops_fast.cuh"
+#include <algorithm>
 
 namespace genrl {
 
@@ -73,6 +75,80 @@ __global__ void __launch_bounds__(256) permute_abp_kernel(const TI* __restrict__
   }
 }
 
+
+// ---- fast paths -------------------------------------------------------------------------------------------------
+// For a fixed output pixel m and filter row kh the k*C elements (kw, c) are contiguous in NHWC memory AND in the col row,
+// so im2col is a set of contiguous segment copies: one 8-element vector per thread when C % 8 == 0.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_vec_kernel(const T* __restrict__ x, T* __restrict__ col, long long ldcol, int N, int H, int W, int C,
+                                                         int k, int Ho, int Wo) {
+  const int seg8 = k * C / 8;
+  const long long total = (long long)N * Ho * Wo * k * seg8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int q = (int)(i % seg8);
+    const int kh = (int)((i / seg8) % k);
+    const long long m = i / ((long long)seg8 * k);
+    const int ow = (int)(m % Wo); const int oh = (int)((m / Wo) % Ho); const long long n = m / ((long long)Wo * Ho);
+    float v[8];
+    V8<T>::load(x + ((n * H + 2 * oh + kh) * W + 2 * ow) * C + q * 8, v);
+    V8<T>::store(col + m * ldcol + (long long)kh * k * C + q * 8, v);
+  }
+}
+
+// generic segment kernel: one thread per (m, kh), scalar inner loop (first layer uint8 NCHW, 3-channel images)
+template <typename TI, typename TO, bool U8_NCHW>
+__global__ void __launch_bounds__(256) im2col_seg_kernel(const TI* __restrict__ x, TO* __restrict__ col, long long ldcol, int N, int H, int W, int C,
+                                                         int k, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * k;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int kh = (int)(i % k);
+    const long long m = i / k;
+    const int ow = (int)(m % Wo); const int oh = (int)((m / Wo) % Ho); const long long n = m / ((long long)Wo * Ho);
+    const int ih = 2 * oh + kh, iw0 = 2 * ow;
+    TO* dst = col + m * ldcol + (long long)kh * k * C;
+    if (U8_NCHW) {
+      const uint8_t* xb = reinterpret_cast<const uint8_t*>(x);
+      for (int c = 0; c < C; ++c) {
+        const uint8_t* src = xb + ((n * C + c) * H + ih) * W + iw0;
+        for (int kw = 0; kw < k; ++kw) dst[kw * C + c] = from_f32<TO>((float)src[kw] / 255.0f - 0.5f);
+      }
+    } else {
+      const TI* src = x + ((n * H + ih) * W + iw0) * C;
+      for (int e = 0; e < k * C; ++e) dst[e] = from_f32<TO>(to_f32(src[e]));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_vec_kernel(const T* __restrict__ col, long long ldcol, const float* __restrict__ bias, T* __restrict__ y,
+                                                         int N, int Hi, int Wi, int C, int k, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const long long total = (long long)N * Ho * Wo * C8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int c = (int)(i % C8) * 8;
+    const int ow = (int)((i / C8) % Wo); const int oh = (int)((i / ((long long)C8 * Wo)) % Ho); const long long n = i / ((long long)C8 * Wo * Ho);
+    float acc[8];
+    if (bias) ldf8(bias + c, acc);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    }
+    for (int kh = oh & 1; kh < k && kh <= oh; kh += 2) {
+      const int ih = (oh - kh) >> 1;
+      if (ih >= Hi) continue;
+      for (int kw = ow & 1; kw < k && kw <= ow; kw += 2) {
+        const int iw = (ow - kw) >> 1;
+        if (iw >= Wi) continue;
+        float v[8];
+        V8<T>::load(col + ((n * Hi + ih) * Wi + iw) * ldcol + (long long)(kh * k + kw) * C + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
+    V8<T>::store(y + ((n * Ho + oh) * (long long)Wo + ow) * C + c, acc);
+  }
+}
+
 static inline unsigned grid_for(long long total) {
   long long g = (total + 255) / 256;
   return (unsigned)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g));
@@ -89,15 +165,22 @@ extern "C" int genrl_im2col(void* stream, const void* x, int x_dtype, void* col,
   const long long total = (long long)N * Ho * Wo * k * k * C;
   if (total <= 0) return 0;
   GENRL_REQUIRE(2 * (Ho - 1) + k <= H && 2 * (Wo - 1) + k <= W, "im2col: output grid %dx%d exceeds input %dx%d (k=%d)", Ho, Wo, H, W, k);
-  unsigned g = grid_for(total);
   cudaStream_t st = ST(stream);
+  const long long segs = (long long)N * Ho * Wo * k;
   if (x_dtype == -1) {
-    if (col_dtype == GENRL_F32) im2col_kernel<uint8_t, float, true><<<g, 256, 0, st>>>((const uint8_t*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
-    else im2col_kernel<uint8_t, __nv_bfloat16, true><<<g, 256, 0, st>>>((const uint8_t*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    if (col_dtype == GENRL_F32) im2col_seg_kernel<uint8_t, float, true><<<grid_for(segs), 256, 0, st>>>((const uint8_t*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    else im2col_seg_kernel<uint8_t, __nv_bfloat16, true><<<grid_for(segs), 256, 0, st>>>((const uint8_t*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
   } else {
     GENRL_REQUIRE(x_dtype == col_dtype, "im2col: dtype mismatch");
-    if (col_dtype == GENRL_F32) im2col_kernel<float, float, false><<<g, 256, 0, st>>>((const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
-    else im2col_kernel<__nv_bfloat16, __nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    if (col_dtype == GENRL_F32) {
+      if (C % 8 == 0 && vec_ok<float>(x, C) && vec_ok<float>(col, ldcol))
+        im2col_vec_kernel<float><<<grid_for(total / 8), 256, 0, st>>>((const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+      else im2col_seg_kernel<float, float, false><<<grid_for(segs), 256, 0, st>>>((const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    } else {
+      if (C % 8 == 0 && vec_ok<__nv_bfloat16>(x, C) && vec_ok<__nv_bfloat16>(col, ldcol))
+        im2col_vec_kernel<__nv_bfloat16><<<grid_for(total / 8), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+      else im2col_seg_kernel<__nv_bfloat16, __nv_bfloat16, false><<<grid_for(segs), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    }
   }
   return check_launch("im2col");
 }
@@ -115,8 +198,16 @@ extern "C" int genrl_col2im(void* stream, const void* col, long long ldcol, int 
     else col2im_kernel<__nv_bfloat16, float, true><<<g, 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
   } else {
     GENRL_REQUIRE(y_dtype == col_dtype, "col2im: dtype mismatch");
-    if (col_dtype == GENRL_F32) col2im_kernel<float, float, false><<<g, 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
-    else col2im_kernel<__nv_bfloat16, __nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
+    const bool bias_ok = bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    if (col_dtype == GENRL_F32) {
+      if (C % 8 == 0 && bias_ok && vec_ok<float>(col, ldcol) && vec_ok<float>(y, C))
+        col2im_vec_kernel<float><<<grid_for(total / 8), 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+      else col2im_kernel<float, float, false><<<g, 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+    } else {
+      if (C % 8 == 0 && bias_ok && vec_ok<__nv_bfloat16>(col, ldcol) && vec_ok<__nv_bfloat16>(y, C))
+        col2im_vec_kernel<__nv_bfloat16><<<grid_for(total / 8), 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
+      else col2im_kernel<__nv_bfloat16, __nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
+    }
   }
   return check_launch("col2im");
 }

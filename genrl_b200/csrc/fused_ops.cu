@@ -3,6 +3,8 @@
 // All are HBM-bound: one warp per row, coalesced loads, fp32 math, activations stored as T (fp32 | bf16).
 // Each forward has a hand-written backward (no autograd inside the library).
 #include "common.cuh"
+#include "rowops_fast.cuh"
+#include <algorithm>
 
 namespace genrl {
 
@@ -648,10 +650,22 @@ __global__ void gather_rows_kernel(const TI* __restrict__ src, long long lds, co
 using namespace genrl;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+static inline bool f32_vec_ok(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int ln_lpr(int D) { int l = 4; while (l * 32 < D) l *= 2; return l; }
+
 extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
                                 void* y, long long ldy, float* stats, long long M, int D, int dtype) {
   if (M <= 0) return 0;
-  DISPATCH_T(dtype, (ln_act_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D)));
+  DISPATCH_T(dtype, {
+    if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(y, ldy) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+      const int lpr = ln_lpr(D);
+      const long long rpb = 8 * (32 / lpr);
+      const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
+      ln_fwd_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
+    } else {
+      ln_act_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D);
+    }
+  });
   return check_launch("ln_act_fwd");
 }
 
@@ -662,25 +676,43 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   GENRL_REQUIRE(3 * D * 4 <= 200 * 1024, "ln_act_bwd: D too large");
   size_t smem = (size_t)3 * D * sizeof(float);
   DISPATCH_T(dtype, {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ln_act_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx,
-                                                                              lddx, dgamma, dbeta, dlin_bias, M, D);
+    if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+      const int lpr = ln_lpr(D);
+      const long long rpb = 8 * (32 / lpr);
+      const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
+      ln_bwd_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+      if (dgamma || dlin_bias) {
+        dim3 g2(ceil_div(M, COL_RC), ceil_div(D, 32));
+        ln_colgrad_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act, dgamma,
+                                                        dbeta, dlin_bias, M, D);
+      }
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      ln_act_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx,
+                                                                                lddx, dgamma, dbeta, dlin_bias, M, D);
+    }
   });
   return check_launch("ln_act_bwd");
 }
 
 extern "C" int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype) {
   if (M <= 0) return 0;
-  long long rpb = 256;
-  dim3 grid(ceil_div(D, 256), ceil_div(M, rpb));
-  DISPATCH_T(dtype, (colsum_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D, rpb)));
+  dim3 grid(ceil_div(M, COL_RC), ceil_div(D, 32));
+  DISPATCH_T(dtype, (colsum_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D)));
   return check_launch("colsum");
 }
 
 extern "C" int genrl_gru_fwd(void* stream, const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
                              float* hout, long long ldho, void* hout_t, long long ldht, float* stats, long long M, int D, int dtype) {
   if (M <= 0) return 0;
-  DISPATCH_T(dtype, (gru_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D)));
+  DISPATCH_T(dtype, {
+    if (D % 8 == 0 && vec_ok<T>(z, ldz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(hout, ldho) && (!hout_t || vec_ok<T>(hout_t, ldht)) &&
+        f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+      gru_fwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
+    } else {
+      gru_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
+    }
+  });
   return check_launch("gru_fwd");
 }
 
@@ -691,9 +723,15 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
   size_t smem = (size_t)6 * D * sizeof(float);
   GENRL_REQUIRE(smem <= 200 * 1024, "gru_bwd: D too large");
   DISPATCH_T(dtype, {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(gru_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gru_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
-                                                                           dhprev, lddhp, dgamma, dbeta, M, D);
+    if (!dgamma && D % 8 == 0 && vec_ok<T>(z, ldz) && vec_ok<T>(dz, lddz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(dh, lddh) &&
+        (!dhprev || vec_ok<float>(dhprev, lddhp)) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+      gru_bwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+                                                                           dhprev, lddhp, M, D);
+    } else {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(gru_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      gru_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+                                                                             dhprev, lddhp, dgamma, dbeta, M, D);
+    }
   });
   return check_launch("gru_bwd");
 }
@@ -790,26 +828,37 @@ extern "C" int genrl_mean_std(void* stream, const float* x, long long n, float* 
 }
 
 // dst[r, 0:cols] = cast(src[r, 0:cols]) * row_scale[r]      dtypes: GENRL_F32 / GENRL_BF16 each side
-extern "C" int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
-                            int cols, const float* row_scale) {
-  if (rows <= 0 || cols <= 0) return 0;
+template <typename TI, typename TO>
+static bool try_fast_gather(cudaStream_t st, const void* src, long long lds, const int* idx, const float* scale, void* dst, long long ldd, long long rows,
+                            int cols, int accumulate) {
+  if (cols % 8 != 0 || !vec_ok<TI>(src, lds) || !vec_ok<TO>(dst, ldd)) return false;
+  const long long total = rows * (cols / 8);
+  const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+  gather_rows_fast_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols / 8, accumulate);
+  return true;
+}
+
+template <typename TI, typename TO>
+static void run_gather(cudaStream_t st, const void* src, long long lds, const int* idx, const float* scale, void* dst, long long ldd, long long rows,
+                       int cols, int accumulate) {
+  if (try_fast_gather<TI, TO>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate)) return;
   unsigned grid = (unsigned)ceil_div(rows * cols, 256);
-  cudaStream_t st = ST(stream);
-  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) copy2d_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, rows, cols, row_scale);
-  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) copy2d_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols, row_scale);
-  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) copy2d_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (float*)dst, ldd, rows, cols, row_scale);
-  else copy2d_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst, ldd, rows, cols, row_scale);
-  return check_launch("copy2d");
+  gather_rows_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols, accumulate);
 }
 
 extern "C" int genrl_gather_rows(void* stream, const void* src, long long lds, int src_dtype, const int* idx, const float* scale, void* dst,
                                  long long ldd, int dst_dtype, long long rows, int cols, int accumulate) {
   if (rows <= 0 || cols <= 0) return 0;
-  unsigned grid = (unsigned)ceil_div(rows * cols, 256);
   cudaStream_t st = ST(stream);
-  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) gather_rows_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, idx, scale, (float*)dst, ldd, rows, cols, accumulate);
-  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) gather_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, lds, idx, scale, (__nv_bfloat16*)dst, ldd, rows, cols, accumulate);
-  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) gather_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, idx, scale, (float*)dst, ldd, rows, cols, accumulate);
-  else gather_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, lds, idx, scale, (__nv_bfloat16*)dst, ldd, rows, cols, accumulate);
+  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) run_gather<float, float>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate);
+  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) run_gather<float, __nv_bfloat16>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate);
+  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) run_gather<__nv_bfloat16, float>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate);
+  else run_gather<__nv_bfloat16, __nv_bfloat16>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate);
   return check_launch("gather_rows");
+}
+
+// dst[r, 0:cols] = cast(src[r, 0:cols]) * row_scale[r]      dtypes: GENRL_F32 / GENRL_BF16 each side
+extern "C" int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
+                            int cols, const float* row_scale) {
+  return genrl_gather_rows(stream, src, lds, src_dtype, nullptr, row_scale, dst, ldd, dst_dtype, rows, cols, 0);
 }

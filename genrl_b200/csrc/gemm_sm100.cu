@@ -110,7 +110,7 @@ struct TcParams {
 };
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, (BN <= 128 ? 2 : 1))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for the 128B swizzle atoms
@@ -388,7 +388,9 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 template <int BN, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams p, int splits, cudaStream_t st) {
   constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;
-  constexpr int STAGES = (BN <= 128) ? 6 : 4;
+  // BN <= 128: 3 stages x <=32 KB -> two CTAs per SM (one CTA's prologue/epilogue overlaps the other's main loop, 6 stages in
+  // flight per SM); wider tiles: 4 stages, one CTA per SM.
+  constexpr int STAGES = (BN <= 128) ? 3 : 4;
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
@@ -407,6 +409,7 @@ static int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, TcP
   switch (bn) {
     case 64: return launch_tc<64, A_MN, B_MN>(ta, tb, p, splits, st);
     case 128: return launch_tc<128, A_MN, B_MN>(ta, tb, p, splits, st);
+    case 160: if constexpr (!B_MN) return launch_tc<160, A_MN, B_MN>(ta, tb, p, splits, st); else return launch_tc<192, A_MN, B_MN>(ta, tb, p, splits, st);
     case 192: return launch_tc<192, A_MN, B_MN>(ta, tb, p, splits, st);
     default: return launch_tc<256, A_MN, B_MN>(ta, tb, p, splits, st);
   }
@@ -423,27 +426,31 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// choose BN and split-K to minimise (waves x tile cost) on the SM count
-static void choose_tiling(int M, int N, int K, bool allow_split, int* bn_out, int* splits_out) {
+// choose BN and split-K with a small cost model (cycles): UMMA 128xBNx16 ~ BN/2 clk -> a 64-deep k-block costs 2*BN clk;
+// prologue+epilogue ~ 1500 + 10*BN clk per tile, overlapped between the two co-resident CTAs when BN <= 128.
+static void choose_tiling(int M, int N, int K, bool allow_split, bool b_mn, int* bn_out, int* splits_out) {
   const int sms = num_sms();
-  const int cands[4] = {64, 128, 192, 256};
+  const int cands[5] = {64, 128, 160, 192, 256};
   const int mt = ceil_div(M, TC_BM);
   const int num_kb = ceil_div(K, TC_BK);
   double best = 1e30;
   int best_bn = 128, best_s = 1;
-  for (int ci = 0; ci < 4; ++ci) {
-    int bn = cands[ci];
+  for (int ci = 0; ci < 5; ++ci) {
+    const int bn = cands[ci];
+    if (b_mn && (bn % 64) != 0) continue;
     if (bn > 64 && bn - 64 >= N) continue;              // needlessly wide
-    int nt = ceil_div(N, bn);
-    int max_s = allow_split ? 16 : 1;
-    for (int s = 1; s <= max_s; s *= 2) {
-      if (s > num_kb) break;
-      long long tiles = (long long)mt * nt * s;
-      long long waves = (tiles + sms - 1) / sms;
-      int kb = ceil_div(num_kb, s);
-      // per-tile cost ~ k-blocks * (MMA cycles ~ bn) + fixed overhead; epilogue ~ bn; atomics penalty for splits
-      double cost = (double)waves * ((double)kb * (bn + 32.0 * (bn <= 64)) + 6.0 * bn + 400.0) * (s > 1 ? 1.05 : 1.0);
+    const int nt = ceil_div(N, bn);
+    for (int s = 1; s <= 512; s *= 2) {
+      if (s > 1 && (!allow_split || num_kb / s < 4)) break;
+      const long long tiles = (long long)mt * nt * s;
+      const long long per_sm = (tiles + sms - 1) / sms;
+      const int kb = ceil_div(num_kb, s);
+      const double mma = (double)per_sm * kb * 2.0 * bn;
+      const double ovh = (1500.0 + 10.0 * bn) * (bn <= 128 ? (double)((per_sm + 1) / 2) : (double)per_sm);
+      const double atom = s > 1 ? 4.0 * bn * per_sm : 0.0;                       // atomic epilogue
+      const double cost = mma + ovh + atom;
       if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+      if (tiles >= 2 * sms) break;
     }
   }
   *bn_out = best_bn;
@@ -482,7 +489,7 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
   GENRL_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "genrl_gemm: bf16 leading dimensions must be multiples of 8 (lda=%lld ldw=%lld)", lda, ldw);
   GENRL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "genrl_gemm: operands must be 16B aligned");
   int bn, splits;
-  choose_tiling(M, N, K, accumulate != 0 && c_dtype == GENRL_F32, &bn, &splits);
+  choose_tiling(M, N, K, c_dtype == GENRL_F32, transW != 0, &bn, &splits);
   CUtensorMap ta, tb;
   if (!transA) { if (make_map(&ta, A, M, K, lda, 64, TC_BM)) return 1; }
   else         { if (make_map(&ta, A, K, M, lda, 64, 64)) return 1; }
@@ -490,10 +497,14 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
   else         { if (make_map(&tb, W, K, N, ldw, 64, 64)) return 1; }
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = (int)ldc; p.c_dtype = c_dtype; p.accumulate = accumulate;
-  p.atomic = splits > 1;
   p.num_kb = ceil_div(K, TC_BK);
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.atomic = splits > 1;
+  if (p.atomic && !accumulate) {           // split-K partial sums are added atomically: start from zero
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st);
+    GENRL_REQUIRE(e == cudaSuccess, "genrl_gemm: memset failed: %s", cudaGetErrorString(e));
+  }
   p.bias = bias; p.C = C;
   if (!transA && !transW) return dispatch_bn<false, false>(bn, ta, tb, p, splits, st);
   if (!transA && transW) return dispatch_bn<false, true>(bn, ta, tb, p, splits, st);
