@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--action-dim", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
     return ap.parse_args()
 
 
@@ -167,6 +168,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg, obs_space, act_spec = make_cfg(args, dev, args.precision)
+    cfg.cuda_graph = not args.eager
     torch.manual_seed(1)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -203,14 +205,15 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    for i in range(max(args.warmup, 3)):
+    l_before = lib.launches
+    step(devb[0], 0)                                        # first call is always eager: count the kernels of one step
+    launches = lib.launches - l_before
+    for i in range(1, max(args.warmup, 3)):
         step(devb[i % nb], i)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = lib.launches
     ms_step = timed(lambda i: step(devb[i % nb], i), args.steps)
-    launches = (lib.launches - l0) // max(1, args.steps)
 
     # end-to-end: host (pinned) batch -> device copy, public API call, device -> host read of the loss, every step
     d2h_bytes = 4
@@ -231,18 +234,25 @@ def run_native(args):
             "gpu_launches": int(launches), "clocks": clk}
 
     if rank == 0 and not args.no_roofline:
-        line["roofline"], line["kernel_breakdown"] = roofline_pass(step, devb, nb, lib, args)
+        line["roofline"], line["kernel_breakdown"] = roofline_pass(step, devb, nb, lib, args, agent)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, agent)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL work: drop them, drain the device, and leave without the (blocking) communicator teardown
+        agent._graphs.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
-def roofline_pass(step, devb, nb, lib, args):
-    """per-kernel CUDA-event timing of two instrumented steps (events on the launching stream around every C-ABI call)"""
+def roofline_pass(step, devb, nb, lib, args, agent):
+    """per-kernel CUDA-event timing of two instrumented EAGER steps (events on the launching stream around every C-ABI call;
+    the graph-captured steps of the timed region cannot be instrumented per kernel)"""
     pk = peaks()
+    graphs_on, agent.cfg.cuda_graph = agent.cfg.cuda_graph, False
     step(devb[0], 0)
     torch.cuda.synchronize()
     lib.profile = []
@@ -251,6 +261,7 @@ def roofline_pass(step, devb, nb, lib, args):
         step(devb[i % nb], i)
     torch.cuda.synchronize()
     prof, lib.profile = lib.profile, None
+    agent.cfg.cuda_graph = graphs_on
     agg = {}
     for name, e0, e1, a, _all in prof:
         d = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..graphs import GraphedCall
 from ..store import ParamStore
 from . import dreamer_utils as common
 
@@ -57,6 +58,7 @@ class DreamerAgent(Module):
         self.requires_grad_(requires_grad=False)
         self._store = None
         self._store_sig = None
+        self._graphs = {}
         self.dp = None                      # genrl_b200.dist.DataParallel when running one process per GPU
 
     # ---- flat parameter store (lazy: train.py swaps sub-modules after construction) ----
@@ -100,6 +102,7 @@ class DreamerAgent(Module):
                     g.m.copy_(prev[0]); g.v.copy_(prev[1]); g.state.copy_(prev[2])
         self._store, self._store_sig = store, sig
         self._store_state = None
+        self._graphs = {}                   # captured graphs hold pointers into the old flat buffers
         opts = [self.wm.model_opt]
         for attr in ("_acting_behavior", "_imag_behavior"):
             beh = getattr(self, attr, None)
@@ -115,6 +118,7 @@ class DreamerAgent(Module):
         st = state.pop("_store", None)
         state["_store"] = None
         state["_store_sig"] = None
+        state["_graphs"] = {}
         state["dp"] = None
         if st is not None:
             state["_store_state"] = {k: (g.m.clone(), g.v.clone(), g.state.clone()) for k, g in st.groups.items() if g.trainable}
@@ -146,14 +150,54 @@ class DreamerAgent(Module):
             action = actor.mean if eval_mode else actor.sample()
             return action.cpu().numpy()[0], (latent, action)
 
+    # ---- CUDA-graph plumbing: cfg.cuda_graph=True captures each update call after two eager warm-ups ----
+    def _use_graphs(self):
+        return bool(getattr(self.cfg, "cuda_graph", False)) and isinstance(ops.noise, ops.PhiloxNoise)
+
+    def _run(self, key, fn, *args):
+        if not self._use_graphs():
+            return fn(*args)
+        gc = self._graphs.get(key)
+        if gc is None:
+            gc = self._graphs[key] = GraphedCall(fn)
+        return gc(*args)
+
+    _WM_KEYS = ("observation", "action", "reward", "is_first", "clip_video")
+
+    def _update_wm_impl(self, data):
+        ops.noise_tick(self.device)
+        return self.wm.update(data, state=None)
+
     def update_wm(self, data, step):
         metrics = {}
         with self._ctx():
             self.ensure_store()
-            state, outputs, mets = self.wm.update(data, state=None)
+            used = {k: data[k] for k in self._WM_KEYS if k in data}
+            state, outputs, mets = self._run("wm", self._update_wm_impl, used)
+        outputs = dict(outputs)
         outputs["is_terminal"] = data["is_terminal"]
         metrics.update(mets)
         return state, outputs, metrics
+
+    def _behavior_impl(self, attr, fn_name, post):
+        ops.noise_tick(self.device)
+        beh = getattr(self, attr)
+        start = {k: stop_gradient(v) for k, v in post.items()}
+        reward_fn = self._reward_closure(fn_name)
+        return beh.update(self.wm, start, None, reward_fn, slow_target=False)
+
+    def _reward_closure(self, fn_name):
+        if callable(fn_name):
+            return lambda seq: fn_name(self, seq)
+        if fn_name == getattr(self.cfg, "imag_reward_fn", None) and fn_name != self.cfg.acting_reward_fn:
+            return lambda seq: _REWARD_FNS[fn_name](self, seq, **self.cfg.imag_reward_args)
+        return lambda seq: _REWARD_FNS[fn_name](self, seq)
+
+    def _update_behavior(self, attr, fn_name, post):
+        key = (attr, fn_name if isinstance(fn_name, str) else id(fn_name))
+        mets = self._run(key, lambda p: self._behavior_impl(attr, fn_name, p), post)
+        getattr(self, attr).update_slow_target()          # host-side counter + occasional copy: outside the graph
+        return mets
 
     def update_acting_behavior(self, state=None, outputs=None, metrics={}, data=None, reward_fn=None):
         if self.cfg.only_random_actions:
@@ -162,18 +206,12 @@ class DreamerAgent(Module):
             self.ensure_store()
             if outputs is not None:
                 post = outputs["post"]
-                is_terminal = outputs["is_terminal"]
             else:
                 with torch.no_grad():
                     embed = self.wm.encoder(data)
                     post, _ = self.wm.rssm.observe(embed, data["action"], data["is_first"])
-                is_terminal = data["is_terminal"]
             start = {k: stop_gradient(v) for k, v in post.items()}
-            if reward_fn is None:
-                acting_reward_fn = lambda seq: _REWARD_FNS[self.cfg.acting_reward_fn](self, seq)
-            else:
-                acting_reward_fn = lambda seq: reward_fn(self, seq)
-            metrics.update(self._acting_behavior.update(self.wm, start, is_terminal, acting_reward_fn))
+            metrics.update(self._update_behavior("_acting_behavior", reward_fn or self.cfg.acting_reward_fn, start))
         return start, metrics
 
     def update(self, data, step):
@@ -394,7 +432,7 @@ class ActorCritic(Module):
         for s, d in zip(self.critic.parameters(), self._target_critic.parameters()):
             d.data = s.data.clone()
 
-    def update(self, world_model, start, is_terminal, reward_fn):
+    def update(self, world_model, start, is_terminal, reward_fn, slow_target=True):
         """reference dreamer.py:366-390"""
         metrics = {}
         hor = self.cfg.imag_horizon
@@ -411,7 +449,8 @@ class ActorCritic(Module):
             critic_loss, mets4 = self.critic_loss(seq, target)
             metrics.update(self.critic_opt(critic_loss, self.critic.parameters()))
         metrics.update(**mets1, **mets2, **mets3, **mets4)
-        self.update_slow_target()
+        if slow_target:
+            self.update_slow_target()
         return {f"{self.name}_{k}".strip("_"): v for k, v in metrics.items()}
 
     def reward_ema(self, target):

@@ -341,7 +341,14 @@ class EnsembleRSSM(Module):
         return state["deter"]
 
     def get_feat(self, state):
-        return torch.cat([self.get_stoch(state), self.get_deter(state)], -1)
+        """[stoch_flat | deter] (reference :405-408), assembled directly in the compute dtype (fp32 in the parity mode, bf16 in
+        the tensor-core mode) so that the heads consume it without another cast"""
+        stoch, deter = self.get_stoch(state), self.get_deter(state)
+        if not stoch.is_cuda:
+            return torch.cat([stoch, deter], -1)
+        lead = tuple(deter.shape[:-1])
+        f = ops.concat(stoch.reshape(-1, stoch.shape[-1]), deter.reshape(-1, deter.shape[-1]))
+        return f.reshape(lead + (f.shape[-1],))
 
     def get_dist(self, state, ensemble=False):
         return CatDist(state["logit"])

@@ -63,13 +63,10 @@ class GenRLAgent(DreamerAgent):
             self.ensure_store()
             if outputs is not None:
                 post = outputs["post"]
-                is_terminal = outputs["is_terminal"]
             else:
                 with torch.no_grad():
                     embed = self.wm.encoder(seq_data)
                     post, _ = self.wm.rssm.observe(embed, seq_data["action"], seq_data["is_first"])
-                is_terminal = seq_data["is_terminal"]
             start = {k: stop_gradient(v) for k, v in post.items()}
-            imag_reward_fn = lambda seq: _REWARD_FNS[self.cfg.imag_reward_fn](self, seq, **self.cfg.imag_reward_args)
-            metrics.update(self._imag_behavior.update(self.wm, start, is_terminal, imag_reward_fn))
+            metrics.update(self._update_behavior("_imag_behavior", self.cfg.imag_reward_fn, start))
         return start, metrics

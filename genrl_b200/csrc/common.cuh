@@ -63,6 +63,21 @@ __device__ __forceinline__ float silu_gradf_(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// bf16 mode uses the SFU fast paths (ex2/rcp approximations, ~2 ulp): activations are rounded to bf16 right after anyway.
+template <bool FAST> __device__ __forceinline__ float sigm_t(float x) {
+  if (FAST) return __frcp_rn(1.0f + __expf(-x));
+  return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST> __device__ __forceinline__ float silu_t(float x) { return x * sigm_t<FAST>(x); }
+template <bool FAST> __device__ __forceinline__ float silu_grad_t(float x) {
+  float s = sigm_t<FAST>(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+template <bool FAST> __device__ __forceinline__ float tanh_t(float x) {
+  if (FAST) return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
+  return tanhf(x);
+}
+
 // Philox4x32-10 counter-based generator (fast-mode noise; parity mode takes explicit noise pointers).
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -243,11 +243,13 @@ constexpr int KPL = 2;   // classes per lane -> K <= 64
 
 template <typename T>
 __global__ void __launch_bounds__(THREADS) cat_sample_fwd_kernel(const float* __restrict__ logit, const float* __restrict__ noise,
-                                                                 unsigned long long seed, unsigned long long offset, int sample,
+                                                                 unsigned long long seed, unsigned long long offset,
+                                                                 const unsigned long long* __restrict__ step_dev, int sample,
                                                                  T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
                                                                  long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S, int K) {
   const int lane = threadIdx.x & 31;
   const long long total = rows * S;
+  if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;     // fresh stream every optimisation step (CUDA-graph safe)
   for (long long g = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * WARPS) {
     const float* lg = logit + g * K;
     float p[KPL], pi[KPL], usum;
@@ -645,6 +647,23 @@ __global__ void gather_rows_kernel(const TI* __restrict__ src, long long lds, co
   *o = from_f32<TO>(accumulate ? to_f32(*o) + v : v);
 }
 
+// standard-normal fill (Box-Muller on Philox4x32-10): actor rsample noise, LAFITE noise of the connector
+__global__ void __launch_bounds__(256) fill_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                                                          const unsigned long long* __restrict__ step_dev) {
+  if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;
+  const long long quads = (n + 3) / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < quads; i += (long long)gridDim.x * 256) {
+    uint4 r = philox4x32(make_uint4((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32) ^ 0x5EEDu),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    float u0 = u32_to_unit_open(r.x), u1 = u32_to_unit_open(r.y), u2 = u32_to_unit_open(r.z), u3 = u32_to_unit_open(r.w);
+    float m0 = sqrtf(-2.0f * logf(u0)), m1 = sqrtf(-2.0f * logf(u2));
+    float z[4] = {m0 * cospif(2.0f * u1), m0 * sinpif(2.0f * u1), m1 * cospif(2.0f * u3), m1 * sinpif(2.0f * u3)};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i * 4 + k < n) out[i * 4 + k] = z[k];
+  }
+}
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+
 }  // namespace genrl
 
 using namespace genrl;
@@ -737,11 +756,11 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
 }
 
 extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset,
-                                    int sample, void* stoch, long long ld_stoch, float* stoch32, long long ld_stoch32, int* idx, long long rows,
+                                    const unsigned long long* step_dev, int sample, void* stoch, long long ld_stoch, float* stoch32, long long ld_stoch32, int* idx, long long rows,
                                     int S, int K, int dtype) {
   if (rows <= 0) return 0;
   GENRL_REQUIRE(K <= 32 * KPL, "cat_sample: K=%d > %d unsupported", K, 32 * KPL);
-  DISPATCH_T(dtype, (cat_sample_fwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, noise, seed, offset, sample, (T*)stoch, ld_stoch,
+  DISPATCH_T(dtype, (cat_sample_fwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
                                                                                                      stoch32, ld_stoch32, idx, rows, S, K)));
   return check_launch("cat_sample_fwd");
 }
@@ -861,4 +880,17 @@ extern "C" int genrl_gather_rows(void* stream, const void* src, long long lds, i
 extern "C" int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
                             int cols, const float* row_scale) {
   return genrl_gather_rows(stream, src, lds, src_dtype, nullptr, row_scale, dst, ldd, dst_dtype, rows, cols, 0);
+}
+
+extern "C" int genrl_fill_normal(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset,
+                                 const unsigned long long* step_dev) {
+  if (n <= 0) return 0;
+  unsigned grid = (unsigned)std::min<long long>(((n + 3) / 4 + 255) / 256, 148 * 16);
+  fill_normal_kernel<<<grid, 256, 0, ST(stream)>>>(out, n, seed, offset, step_dev);
+  return check_launch("fill_normal");
+}
+
+extern "C" int genrl_counter_add(void* stream, unsigned long long* counter, unsigned long long inc) {
+  counter_add_kernel<<<1, 1, 0, ST(stream)>>>(counter, inc);
+  return check_launch("counter_add");
 }

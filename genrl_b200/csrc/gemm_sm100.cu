@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <algorithm>
 
 namespace genrl {
 
@@ -426,8 +427,10 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// choose BN and split-K with a small cost model (cycles): UMMA 128xBNx16 ~ BN/2 clk -> a 64-deep k-block costs 2*BN clk;
-// prologue+epilogue ~ 1500 + 10*BN clk per tile, overlapped between the two co-resident CTAs when BN <= 128.
+// choose BN and split-K with a small cost model in SM cycles.  At these sizes the kernel is bound by the L2->SM operand feed, not
+// by the tensor pipe: a 128xBN tile moves (128+BN)*128 B per 64-deep k-block for 2*BN cycles of UMMA work, against a chip-wide L2
+// cap of ~6300 B/clk (B300_MICROARCH.md) and ~96 B/clk per SM.  BN <= 128 runs two CTAs per SM, so one CTA's prologue/epilogue
+// (~1500 + 8*BN clk) hides behind the other's main loop.
 static void choose_tiling(int M, int N, int K, bool allow_split, bool b_mn, int* bn_out, int* splits_out) {
   const int sms = num_sms();
   const int cands[5] = {64, 128, 160, 192, 256};
@@ -445,12 +448,14 @@ static void choose_tiling(int M, int N, int K, bool allow_split, bool b_mn, int*
       const long long tiles = (long long)mt * nt * s;
       const long long per_sm = (tiles + sms - 1) / sms;
       const int kb = ceil_div(num_kb, s);
+      const double bytes_cta = (double)kb * (128.0 + bn) * 128.0;
       const double mma = (double)per_sm * kb * 2.0 * bn;
-      const double ovh = (1500.0 + 10.0 * bn) * (bn <= 128 ? (double)((per_sm + 1) / 2) : (double)per_sm);
-      const double atom = s > 1 ? 4.0 * bn * per_sm : 0.0;                       // atomic epilogue
-      const double cost = mma + ovh + atom;
+      const double mem = std::max((double)tiles * bytes_cta / 6300.0, (double)per_sm * bytes_cta / 96.0);
+      const double ovh = (1500.0 + 8.0 * bn) * (bn <= 128 ? (double)((per_sm + 1) / 2) : (double)per_sm);
+      const double atom = s > 1 ? 6.0 * bn * per_sm : 0.0;                       // atomic epilogue
+      const double cost = std::max(mma, mem) + ovh + atom;
       if (cost < best) { best = cost; best_bn = bn; best_s = s; }
-      if (tiles >= 2 * sms) break;
+      if (tiles >= 4 * sms) break;
     }
   }
   *bn_out = best_bn;

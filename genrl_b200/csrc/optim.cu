@@ -218,7 +218,7 @@ extern "C" int genrl_adam_step(void* stream, float* p, float* g, float* m, float
 // table: device array of PackEntry (see genrl_b200.h for the field layout), n_entries launches in one grid
 extern "C" int genrl_pack_weights(void* stream, const void* table, int n_entries, int dst_dtype) {
   if (n_entries <= 0) return 0;
-  dim3 grid(64, n_entries);
+  dim3 grid(148 * 2, n_entries);
   if (dst_dtype == GENRL_F32) pack_kernel<float><<<grid, 256, 0, ST(stream)>>>((const PackEntry*)table);
   else pack_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>((const PackEntry*)table);
   return check_launch("pack_weights");

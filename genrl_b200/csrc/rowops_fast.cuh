@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) ln_fwd_fast_kernel(const T* __restrict__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float a = (v[i][j] - mean) * rstd * g[j] + b[j];
-            o[j] = act == GENRL_ACT_SILU ? siluf_(a) : a;
+            o[j] = act == GENRL_ACT_SILU ? silu_t<(sizeof(T) == 2)>(a) : a;
           }
           V8<T>::store(y + row * ldy + c, o);
         }
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) ln_bwd_fast_kernel(const T* __restrict__ 
         for (int j = 0; j < 8; ++j) {
           float h = (xh[i][j] - mean) * rstd;
           float gg = d[j];
-          if (act == GENRL_ACT_SILU) gg *= silu_gradf_(h * g[j] + b[j]);
+          if (act == GENRL_ACT_SILU) gg *= silu_grad_t<(sizeof(T) == 2)>(h * g[j] + b[j]);
           gg *= g[j];
           xh[i][j] = h; gh[i][j] = gg;
           s1 += gg; s2 += gg * h;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) ln_bwd_fast_kernel(const T* __restrict__ 
 }
 
 // ---- column pass of the LayerNorm backward: dgamma/dbeta/dlin_bias += column sums over a chunk of rows --------------
-constexpr int COL_RC = 128;   // rows per block
+constexpr int COL_RC = 256;   // rows per block
 template <typename T>
 __global__ void __launch_bounds__(256) ln_colgrad_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
                                                          const T* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
@@ -169,11 +169,12 @@ __global__ void __launch_bounds__(256) ln_colgrad_kernel(const T* __restrict__ d
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   if (c < D) {
     const float g = gamma[c], b = beta[c];
+#pragma unroll 8
     for (long long r = r0 + ty; r < r1; r += 8) {
       if (dgamma) {
         float h = (to_f32(x[r * ldx + c]) - stats[r * 2]) * stats[r * 2 + 1];
         float gg = to_f32(dy[r * lddy + c]);
-        if (act == GENRL_ACT_SILU) gg *= silu_gradf_(h * g + b);
+        if (act == GENRL_ACT_SILU) gg *= silu_grad_t<(sizeof(T) == 2)>(h * g + b);
         a0 += gg * h; a1 += gg;
       }
       if (dlb) a2 += to_f32(dx[r * lddx + c]);
@@ -197,7 +198,10 @@ __global__ void __launch_bounds__(256) colsum_fast_kernel(const T* __restrict__ 
   const int c = blockIdx.y * 32 + tx;
   const long long r0 = (long long)blockIdx.x * COL_RC, r1 = min(M, r0 + COL_RC);
   float a = 0.f;
-  if (c < D) for (long long r = r0 + ty; r < r1; r += 8) a += to_f32(x[r * ldx + c]);
+  if (c < D) {
+#pragma unroll 8
+    for (long long r = r0 + ty; r < r1; r += 8) a += to_f32(x[r * ldx + c]);
+  }
   red[ty][tx] = a;
   __syncthreads();
   if (ty == 0 && c < D) {
@@ -209,6 +213,7 @@ __global__ void __launch_bounds__(256) colsum_fast_kernel(const T* __restrict__ 
 }
 
 // ---- GRU tail, vectorised (one warp per row; gate parts re-read from L1) ---------------------------------------------
+template <bool FAST>
 __device__ __forceinline__ void gru_gate8(const float (&zr)[8], const float (&zc)[8], const float (&zu)[8], float mean, float rstd,
                                           const float* __restrict__ gamma, const float* __restrict__ beta, int D, int j,
                                           float (&r)[8], float (&cand)[8], float (&u)[8], float (&pc)[8], float (&xr)[8], float (&xc)[8], float (&xu)[8]) {
@@ -221,7 +226,7 @@ __device__ __forceinline__ void gru_gate8(const float (&zr)[8], const float (&zc
     float pr = xr[k] * gr[k] + br[k];
     pc[k] = xc[k] * gc[k] + bc[k];
     float pu = xu[k] * gu[k] + bu[k];
-    r[k] = sigmoidf_(pr); cand[k] = tanhf(r[k] * pc[k]); u[k] = sigmoidf_(pu - 1.0f);
+    r[k] = sigm_t<FAST>(pr); cand[k] = tanh_t<FAST>(r[k] * pc[k]); u[k] = sigm_t<FAST>(pu - 1.0f);
   }
 }
 
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(256) gru_fwd_fast_kernel(const T* __restrict__
     for (int j = lane * 8; j < D; j += 256) {
       float a[8], b[8], c[8], r[8], cand[8], u[8], pc[8], xr[8], xc[8], xu[8], h[8], o[8];
       V8<T>::load(zr_ + j, a); V8<T>::load(zr_ + D + j, b); V8<T>::load(zr_ + 2 * D + j, c);
-      gru_gate8(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
+      gru_gate8<(sizeof(T) == 2)>(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
       ldf8(hprev + row * ldh + j, h);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = u[k] * cand[k] + (1.0f - u[k]) * h[k];
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(256) gru_bwd_fast_kernel(const float* __restri
         float a[8], b[8], c[8], r[8], cand[8], u[8], pc[8], xr[8], xc[8], xu[8], h[8], g[8];
         float gr[8], gc[8], gu[8];
         V8<T>::load(zr_ + j, a); V8<T>::load(zr_ + D + j, b); V8<T>::load(zr_ + 2 * D + j, c);
-        gru_gate8(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
+        gru_gate8<(sizeof(T) == 2)>(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
         ldf8(hprev + row * ldh + j, h); ldf8(dh + row * lddh + j, g);
         ldf8(gamma + j, gr); ldf8(gamma + D + j, gc); ldf8(gamma + 2 * D + j, gu);
         float o1[8], o2[8], o3[8], o4[8];

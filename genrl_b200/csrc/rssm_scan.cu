@@ -32,11 +32,25 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch,
     __threadfence();
     atomicAdd(counter, 1u);
     const unsigned target = epoch * nblocks;
-    while (ld_acquire_u32(counter) < target) { __nanosleep(20); }
+    while (ld_acquire_u32(counter) < target) { }
     __threadfence();
   }
   __syncthreads();
 }
+
+// LayerNorm statistics are exchanged as 64-bit fixed-point atomics: integer addition is associative, so the sum over the
+// grid is deterministic (bit-identical run to run, unlike float atomics) and needs one 16-byte read per row afterwards.
+__device__ __forceinline__ void fx_add(unsigned long long* p, float v, double scale) {
+  const long long q = __double2ll_rn((double)v * scale);
+  atomicAdd(p, (unsigned long long)q);
+}
+__device__ __forceinline__ float fx_get(const unsigned long long* p, double inv_scale) {
+  unsigned long long u;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(u) : "l"(p) : "memory");
+  return (float)((double)(long long)u * inv_scale);
+}
+constexpr double FX_FWD = 17179869184.0;        // 2^34: |sum| < 5e8, resolution 6e-11
+constexpr double FX_BWD = 17592186044416.0;     // 2^44: |sum| < 5e5, resolution 6e-14 (gradient-sized sums)
 
 // after the call lane l holds sum over lanes of v[l]
 __device__ __forceinline__ float reduce_scatter32(float (&v)[32], int lane) {
@@ -58,14 +72,19 @@ template <int R>
 __device__ __forceinline__ void warp_matvec(const float* __restrict__ Ws, int Kd, const float* const (&hrow)[SCAN_RB], const float (&scale)[SCAN_RB],
                                             float (&acc)[SCAN_RB * R], int lane) {
   if ((Kd & 127) == 0) {
+    float4 hn[SCAN_RB];
+#pragma unroll
+    for (int rb = 0; rb < SCAN_RB; ++rb) hn[rb] = hrow[rb] ? __ldcg(reinterpret_cast<const float4*>(hrow[rb] + 4 * lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 4 * lane; k < Kd; k += 128) {
       float4 h[SCAN_RB];
 #pragma unroll
       for (int rb = 0; rb < SCAN_RB; ++rb) {
-        if (hrow[rb]) {
-          h[rb] = __ldcg(reinterpret_cast<const float4*>(hrow[rb] + k));
-          h[rb].x *= scale[rb]; h[rb].y *= scale[rb]; h[rb].z *= scale[rb]; h[rb].w *= scale[rb];
-        } else h[rb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        h[rb] = hn[rb];
+        h[rb].x *= scale[rb]; h[rb].y *= scale[rb]; h[rb].z *= scale[rb]; h[rb].w *= scale[rb];
+      }
+      if (k + 128 < Kd) {                        // prefetch the next slice while this one is multiplied
+#pragma unroll
+        for (int rb = 0; rb < SCAN_RB; ++rb) if (hrow[rb]) hn[rb] = __ldcg(reinterpret_cast<const float4*>(hrow[rb] + k + 128));
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -102,7 +121,7 @@ struct ScanFwdParams {
   void* hprev_t; long long ld_hp;                   // optional masked h_{t-1} in activation dtype ([x|h] operand slice)
   float* z;                   // [B*T, 3D] pre-LayerNorm activations (saved for backward)
   float* stats;               // [B*T, 2]
-  float* partial;             // workspace [2][B][G][2]
+  unsigned long long* fx;     // workspace [T][B][2] fixed-point (sum, sum of squares), zeroed by the host
   unsigned* barrier;          // workspace counter, zeroed by the host
 };
 
@@ -173,30 +192,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
     }
     __syncthreads();
     // ---- phase 2: LayerNorm partial sums of this CTA's 24 values per row ----
-    float* part = p.partial + (size_t)(t & 1) * B * G * 2;
+    unsigned long long* fx = p.fx + (size_t)t * B * 2;
     for (int b = tid; b < B; b += SCAN_THREADS) {
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) { float v = zs[b * R + r]; s1 += v; s2 += v * v; }
-      part[((size_t)b * G + blockIdx.x) * 2] = s1;
-      part[((size_t)b * G + blockIdx.x) * 2 + 1] = s2;
+      fx_add(fx + b * 2, s1, FX_FWD);
+      fx_add(fx + b * 2 + 1, s2, FX_FWD);
     }
     grid_barrier(p.barrier, epoch, G);
-    // ---- phase 3: full-row statistics (fixed summation order -> deterministic) ----
-    for (int b = warp; b < B; b += SCAN_WARPS) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = lane; c < G; c += 32) {
-        float2 v = __ldcg(reinterpret_cast<const float2*>(part + ((size_t)b * G + c) * 2));
-        s1 += v.x; s2 += v.y;
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) {
-        float mean = s1 / D3;
-        float var = fmaxf(s2 / D3 - mean * mean, 0.f);
-        float rstd = 1.0f / sqrtf(var + 1e-5f);
-        st[b * 2] = mean; st[b * 2 + 1] = rstd;
-        if (blockIdx.x == 0) { p.stats[((size_t)b * T + t) * 2] = mean; p.stats[((size_t)b * T + t) * 2 + 1] = rstd; }
-      }
+    // ---- phase 3: full-row statistics ----
+    for (int b = tid; b < B; b += SCAN_THREADS) {
+      float mean = fx_get(fx + b * 2, 1.0 / FX_FWD) / D3;
+      float var = fmaxf(fx_get(fx + b * 2 + 1, 1.0 / FX_FWD) / D3 - mean * mean, 0.f);
+      float rstd = 1.0f / sqrtf(var + 1e-5f);
+      st[b * 2] = mean; st[b * 2 + 1] = rstd;
+      if (blockIdx.x == 0) { p.stats[((size_t)b * T + t) * 2] = mean; p.stats[((size_t)b * T + t) * 2 + 1] = rstd; }
     }
     __syncthreads();
     // ---- phase 4: gates for the owned units ----
@@ -236,7 +247,7 @@ struct ScanBwdParams {
   float* dh0;                 // [B, D] or null
   float* dgamma; float* dbeta;                   // [3D] accumulated (+=), or null
   float* dzf;                 // workspace [2][B][3D] fp32
-  float* partial;             // workspace [2][B][G][2]
+  unsigned long long* fx;     // workspace [T][B][2] fixed-point, zeroed by the host
   unsigned* barrier;
 };
 
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_bwd_kernel(ScanBwdP
 
   const int ngroups = (B + SCAN_RB - 1) / SCAN_RB;
   for (int t = T - 1; t >= 0; --t) {
-    float* part = p.partial + (size_t)(t & 1) * B * G * 2;
+    unsigned long long* fx = p.fx + (size_t)t * B * 2;
     float* dzf = p.dzf + (size_t)(t & 1) * B * D3;
     // ---- phase 1: gate gradients for owned units, LayerNorm-backward partial sums ----
     for (int i = tid; i < B * SCAN_U; i += SCAN_THREADS) {
@@ -293,19 +304,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_bwd_kernel(ScanBwdP
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) { s1 += gs[b * R + r]; s2 += gs[b * R + r] * xs[b * R + r]; }
-      part[((size_t)b * G + blockIdx.x) * 2] = s1;
-      part[((size_t)b * G + blockIdx.x) * 2 + 1] = s2;
+      fx_add(fx + b * 2, s1, FX_BWD);
+      fx_add(fx + b * 2 + 1, s2, FX_BWD);
     }
     grid_barrier(p.barrier, epoch, G);
     // ---- phase 2: dz for owned rows ----
-    for (int b = warp; b < B; b += SCAN_WARPS) {
-      float s1 = 0.f, s2 = 0.f;
-      for (int c = lane; c < G; c += 32) {
-        float2 v = __ldcg(reinterpret_cast<const float2*>(part + ((size_t)b * G + c) * 2));
-        s1 += v.x; s2 += v.y;
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) { st[b * 2] = s1 / D3; st[b * 2 + 1] = s2 / D3; }
+    for (int b = tid; b < B; b += SCAN_THREADS) {
+      st[b * 2] = fx_get(fx + b * 2, 1.0 / FX_BWD) / D3;
+      st[b * 2 + 1] = fx_get(fx + b * 2 + 1, 1.0 / FX_BWD) / D3;
     }
     __syncthreads();
     for (int i = tid; i < B * R; i += SCAN_THREADS) {
@@ -359,9 +365,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_bwd_kernel(ScanBwdP
 using namespace genrl;
 
 extern "C" long long genrl_rssm_scan_workspace_bytes(int B, int T, int D) {
-  (void)T;
-  long long G = D / SCAN_U;
-  return 256 + (long long)2 * B * G * 2 * 4 + (long long)2 * B * 3 * D * 4;
+  // [256 B barrier][T*B*2 u64 fixed-point statistics][2*B*3D fp32 dz staging (backward)]
+  return 256 + (long long)T * B * 2 * 8 + (long long)2 * B * 3 * D * 4;
 }
 
 static int scan_check(int B, int T, int D, const char* who) {
@@ -386,12 +391,12 @@ extern "C" int genrl_rssm_scan_fwd(void* stream, int B, int T, int D, const floa
   p.deter = deter; p.deter_t = deter_t; p.ld_dt = ld_dt; p.t_dtype = t_dtype; p.hprev_t = hprev_t; p.ld_hp = ld_hp;
   p.z = z; p.stats = stats;
   p.barrier = reinterpret_cast<unsigned*>(workspace);
-  p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  p.fx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 256);
   size_t smem = ((size_t)3 * SCAN_U * D + (size_t)B * 3 * SCAN_U + (size_t)B * 2) * sizeof(float);
   GENRL_REQUIRE(smem <= 227 * 1024, "rssm_scan_fwd: %zu bytes of shared memory needed (B=%d D=%d)", smem, B, D);
   cudaError_t e = cudaFuncSetAttribute(rssm_scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_fwd: smem attribute: %s", cudaGetErrorString(e));
-  cudaMemsetAsync(workspace, 0, 256, st);
+  cudaMemsetAsync(workspace, 0, 256 + (size_t)T * B * 16, st);
   void* args[] = {&p};
   e = cudaLaunchCooperativeKernel((void*)rssm_scan_fwd_kernel, dim3(p.G), dim3(SCAN_THREADS), args, smem, st);
   GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
@@ -408,14 +413,14 @@ extern "C" int genrl_rssm_scan_bwd(void* stream, int B, int T, int D, const floa
   p.dh_ext = dh_ext; p.z = z; p.stats = stats; p.Wh = Wh; p.ldw = ldw; p.gamma = gamma; p.beta = beta; p.mask = mask;
   p.deter = deter; p.h0 = h0; p.dz_t = dz_t; p.ld_dz = ld_dz; p.t_dtype = t_dtype; p.dh0 = dh0; p.dgamma = dgamma; p.dbeta = dbeta;
   p.barrier = reinterpret_cast<unsigned*>(workspace);
-  p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
-  p.dzf = p.partial + (size_t)2 * B * p.G * 2;
+  p.fx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 256);
+  p.dzf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256 + (size_t)T * B * 16);
   const int R = 3 * SCAN_U;
   size_t smem = ((size_t)SCAN_U * 3 * D + (size_t)2 * B * R + (size_t)2 * B * SCAN_U + (size_t)B * 2 + 2 * R) * sizeof(float);
   GENRL_REQUIRE(smem <= 227 * 1024, "rssm_scan_bwd: %zu bytes of shared memory needed (B=%d D=%d)", smem, B, D);
   cudaError_t e = cudaFuncSetAttribute(rssm_scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_bwd: smem attribute: %s", cudaGetErrorString(e));
-  cudaMemsetAsync(workspace, 0, 256, st);
+  cudaMemsetAsync(workspace, 0, 256 + (size_t)T * B * 16, st);
   void* args[] = {&p};
   e = cudaLaunchCooperativeKernel((void*)rssm_scan_bwd_kernel, dim3(p.G), dim3(SCAN_THREADS), args, smem, st);
   GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_bwd: cooperative launch failed: %s", cudaGetErrorString(e));

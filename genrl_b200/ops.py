@@ -459,7 +459,8 @@ class _CatSample(Function):
         rows = logit.numel() // (S * K)
         stoch = torch.empty(rows, S * K, device=logit.device, dtype=torch.float32)
         idx = torch.empty(rows, S, device=logit.device, dtype=torch.int32)
-        lib.genrl_cat_sample_fwd(_st(), _p(logit), _p(noise), seed, offset, int(sample), None, 0, _p(stoch), S * K, _p(idx), rows, S, K, F32)
+        step_dev = noise_step_ptr(logit.device) if (noise is None and sample) else None
+        lib.genrl_cat_sample_fwd(_st(), _p(logit), _p(noise), seed, offset, step_dev, int(sample), None, 0, _p(stoch), S * K, _p(idx), rows, S, K, F32)
         ctx.save_for_backward(logit)
         ctx.sample, ctx.S, ctx.K = sample, S, K
         ctx.mark_non_differentiable(idx)
@@ -856,24 +857,36 @@ def gru_scan(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
 # noise providers: in-kernel Philox (product) or an explicit tape of reference draws (parity tests)
 # ---------------------------------------------------------------------------------------------------------------
 class PhiloxNoise:
-    """Fast mode: categorical noise is generated inside the sampling kernel (Philox4x32-10, key = seed, ctr = offset)."""
+    """Fast mode: noise is generated inside the kernels (Philox4x32-10).  key = seed (+ a device-side step counter that
+    `tick()` bumps once per update, so captured CUDA graphs draw fresh noise on every replay), counter = per-call offset."""
 
     def __init__(self, seed=0):
         self.seed = int(seed)
         self.offset = 0
-        self._gen = {}
+        self._step = {}
+
+    def step_counter(self, device):
+        k = str(device)
+        c = self._step.get(k)
+        if c is None:
+            c = torch.zeros(1, device=device, dtype=torch.int64)
+            self._step[k] = c
+        return c
+
+    def tick(self, device):
+        """new update call: bump the device-side key, restart the per-call offsets (identical in eager and graph mode)"""
+        lib.genrl_counter_add(_st(), self.step_counter(device).data_ptr(), 1)
+        self.offset = 0
 
     def exp(self, rows, K, device):
         self.offset += 1
         return None, self.seed, self.offset
 
     def randn(self, shape, device):
-        g = self._gen.get(str(device))
-        if g is None:
-            g = torch.Generator(device=device)
-            g.manual_seed(self.seed + 977)
-            self._gen[str(device)] = g
-        return torch.randn(shape, device=device, dtype=torch.float32, generator=g)
+        self.offset += 1
+        out = torch.empty(shape, device=device, dtype=torch.float32)
+        lib.genrl_fill_normal(_st(), out.data_ptr(), out.numel(), self.seed, self.offset, self.step_counter(device).data_ptr())
+        return out
 
     def randint(self):
         return None
@@ -907,6 +920,9 @@ class TapeNoise:
     def randint(self):
         return self._next("randint")
 
+    def tick(self, device):
+        pass
+
     def observe(self, B, T, S, K, device):
         """reference order per step: randint, prior draw, posterior draw (dreamer_utils.py:437-438, :477)"""
         pri, pos = [], []
@@ -919,6 +935,18 @@ class TapeNoise:
 
 
 noise = PhiloxNoise(0)
+
+
+def noise_step_ptr(device):
+    """device pointer of the step counter that keys the in-kernel generators (None for tape replay)"""
+    if isinstance(noise, PhiloxNoise):
+        return noise.step_counter(device).data_ptr()
+    return None
+
+
+def noise_tick(device):
+    if isinstance(noise, PhiloxNoise):
+        noise.tick(device)
 
 
 def set_noise(provider):

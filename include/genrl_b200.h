@@ -44,11 +44,18 @@ int genrl_gru_bwd(void* stream, const float* dh, long long lddh, const void* z, 
 
 /* OneHotDist sample / mode with straight-through gradient: dreamer_utils.py:177-197, :410-416.
  * noise != NULL: q ~ Exp(1) supplied by the caller (parity mode); else Philox(seed, offset). */
-int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset, int sample,
+int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset,
+                         const unsigned long long* step_dev, int sample,
                          void* stoch, long long ld_stoch, float* stoch32, long long ld_stoch32, int* idx, long long rows, int S, int K,
                          int dtype);
 int genrl_cat_sample_bwd(void* stream, const float* logit, const void* dstoch, long long ld_ds, int sample, float* dlogit, int accumulate,
                          long long rows, int S, int K, int dtype);
+
+/* Philox4x32-10 standard-normal fill (Normal.rsample noise, dreamer_utils.py:814-819; LAFITE noise, video_utils.py:143-146) and
+ * the device-side step counter that keys every in-kernel generator (so CUDA-graph replays draw fresh noise). */
+int genrl_fill_normal(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset,
+                      const unsigned long long* step_dev);
+int genrl_counter_add(void* stream, unsigned long long* counter, unsigned long long inc);
 
 /* EnsembleRSSM.kl_loss + entropies: dreamer_utils.py:534-555, dreamer.py:249-250.  out4 = {loss, mean value, ent lhs, ent rhs}. */
 int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, float free_bits, float* value, float* out4, long long rows, int S, int K);

@@ -116,3 +116,31 @@ def test_agent_fast_noise_pickle_and_act():
     assert action.shape == (meta["A"],) and np.all(np.abs(action) <= 2.0)
     action, st = agent2.act(obs, None, 1, eval_mode=True, state=st)
     assert action.shape == (meta["A"],)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """the graph-captured update (cfg.cuda_graph) reproduces the eager update step for step (same Philox keys)"""
+    from genrl_b200 import ops
+    results = []
+    for graphed in (False, True):
+        agent, data, g, meta = build_agent("tiny_genrl", 32)
+        agent.cfg.cuda_graph = graphed
+        ops.set_noise(ops.PhiloxNoise(77))
+        hist = []
+        for step in range(5):
+            state, outputs, metrics = agent.update_wm(data, step)
+            start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+            hist.append({k: float(torch.as_tensor(v).float().cpu().reshape(-1)[0]) for k, v in metrics.items()})
+            stoch = outputs["post"]["stoch"].clone()
+        results.append((hist, stoch, {k: v.clone() for k, v in agent.state_dict().items()}))
+        if graphed:
+            assert agent._graphs and all(gc.graph is not None for gc in agent._graphs.values()), "graphs were not captured"
+    (h0, s0, p0), (h1, s1, p1) = results
+    assert torch.equal(s0, s1), "sampled latents differ between eager and graph replay"
+    for a, b in zip(h0, h1):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    assert h0[1]["kl_loss"] != h0[2]["kl_loss"]          # the step counter gives fresh noise each step
+    for k in p0:
+        assert torch.allclose(p0[k].float(), p1[k].float(), rtol=1e-3, atol=1e-5), k
+    ops.set_noise(ops.PhiloxNoise(0))
