@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--action-dim", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
     return ap.parse_args()
 
@@ -169,6 +170,7 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
     cfg, obs_space, act_spec = make_cfg(args, dev, args.precision)
     cfg.cuda_graph = not args.eager
+    cfg.overlap_streams = not args.no_overlap
     torch.manual_seed(1)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):

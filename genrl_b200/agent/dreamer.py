@@ -279,6 +279,11 @@ class WorldModel(Module):
     def update(self, data, state=None):
         """reference dreamer.py:166-187"""
         self.train()
+        overlap = getattr(self.cfg, "overlap_streams", False) in (True, "wm") and len(self.detached_update_fns) > 0 and not self.e2e_update_fns
+        if overlap:
+            state, outputs, metrics = self._update_overlapped(data, state)
+            self.eval()
+            return state, outputs, metrics
         with common.RequiresGrad(self):
             model_loss, state, outputs, metrics = self.loss(data, state)
             model_loss, metrics = self.update_additional_e2e_modules(data, outputs, model_loss, metrics)
@@ -288,6 +293,33 @@ class WorldModel(Module):
         if len(self.detached_update_fns) > 0:
             detached_loss, metrics = self.update_additional_detached_modules(data, outputs, metrics)
         self.eval()
+        return state, outputs, metrics
+
+    def _update_overlapped(self, data, state=None):
+        """Same update, two streams: the detached modules' forward+backward (connector: a latency-bound chain of small kernels and
+        the persistent scan) run beside the world model's backward (conv/GEMM heavy).  The optimizer steps keep the reference
+        order (world model, then connector); the only difference is that the connector's forward reads its weights before the
+        world-model step's 1e-6 multiplicative decay instead of after."""
+        main = torch.cuda.current_stream()
+        side = common.side_stream(self.device)
+        with common.RequiresGrad(self):
+            model_loss, state, outputs, metrics = self.loss(data, state)
+            outputs = {k: ({kk: vv.detach() for kk, vv in v.items()} if isinstance(v, dict) else v.detach()) for k, v in outputs.items()}
+            state = {k: v.detach() for k, v in state.items()}
+            side.wait_stream(main)
+            det = []
+            with torch.cuda.stream(side):
+                for k in self.detached_update_fns:
+                    add_loss, add_metrics = self.detached_update_fns[k](self, k, data, outputs, metrics)
+                    self.model_opt.backward(add_loss)
+                    det.append((k, add_loss, add_metrics))
+            self.model_opt.backward(model_loss)
+            main.wait_stream(side)
+            metrics.update(self.model_opt.apply(model_loss, self.parameters()))
+            for k, add_loss, add_metrics in det:
+                metrics.update(add_metrics)
+                opt_metrics = self.model_opt.apply(add_loss, getattr(self, k).parameters())
+                metrics.update({f"{k}_{m}": opt_metrics[m] for m in opt_metrics})
         return state, outputs, metrics
 
     def update_additional_detached_modules(self, data, outputs, metrics):
@@ -436,18 +468,39 @@ class ActorCritic(Module):
         """reference dreamer.py:366-390"""
         metrics = {}
         hor = self.cfg.imag_horizon
-        with common.RequiresGrad(self.actor):
-            seq = world_model.imagine(self.actor, start, is_terminal, hor)
-            reward = reward_fn(seq)
-            seq["reward"], mets1 = self.rewnorm(reward)
-            mets1 = {f"reward_{k}": v for k, v in mets1.items()}
-            target, mets2, baseline = self.target(seq)
-            actor_loss, mets3 = self.actor_loss(seq, target, baseline)
-            metrics.update(self.actor_opt(actor_loss, self.actor.parameters()))
-        with common.RequiresGrad(self.critic):
-            seq = {k: stop_gradient(v) for k, v in seq.items()}
-            critic_loss, mets4 = self.critic_loss(seq, target)
-            metrics.update(self.critic_opt(critic_loss, self.critic.parameters()))
+        if getattr(self.cfg, "overlap_streams", False) in (True, "beh"):
+            # critic forward+backward (large 36 000-row kernels) on a second stream beside the actor's backward through the rollout
+            main = torch.cuda.current_stream()
+            side = common.side_stream(self.device)
+            with common.RequiresGrad(self.actor), common.RequiresGrad(self.critic):
+                seq = world_model.imagine(self.actor, start, is_terminal, hor)
+                reward = reward_fn(seq)
+                seq["reward"], mets1 = self.rewnorm(reward)
+                mets1 = {f"reward_{k}": v for k, v in mets1.items()}
+                target, mets2, baseline = self.target(seq)
+                actor_loss, mets3 = self.actor_loss(seq, target, baseline)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    seq_d = {k: stop_gradient(v) for k, v in seq.items()}
+                    critic_loss, mets4 = self.critic_loss(seq_d, target)
+                    self.critic_opt.backward(critic_loss)
+                self.actor_opt.backward(actor_loss)
+                main.wait_stream(side)
+                metrics.update(self.actor_opt.apply(actor_loss, self.actor.parameters()))
+                metrics.update(self.critic_opt.apply(critic_loss, self.critic.parameters()))
+        else:
+            with common.RequiresGrad(self.actor):
+                seq = world_model.imagine(self.actor, start, is_terminal, hor)
+                reward = reward_fn(seq)
+                seq["reward"], mets1 = self.rewnorm(reward)
+                mets1 = {f"reward_{k}": v for k, v in mets1.items()}
+                target, mets2, baseline = self.target(seq)
+                actor_loss, mets3 = self.actor_loss(seq, target, baseline)
+                metrics.update(self.actor_opt(actor_loss, self.actor.parameters()))
+            with common.RequiresGrad(self.critic):
+                seq = {k: stop_gradient(v) for k, v in seq.items()}
+                critic_loss, mets4 = self.critic_loss(seq, target)
+                metrics.update(self.critic_opt(critic_loss, self.critic.parameters()))
         metrics.update(**mets1, **mets2, **mets3, **mets4)
         if slow_target:
             self.update_slow_target()

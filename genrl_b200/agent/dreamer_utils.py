@@ -618,15 +618,34 @@ class Optimizer:
         self.allreduce = None          # set by the data-parallel wrapper
 
     def __call__(self, loss, params):
-        params = list(params)
+        self.backward(loss)
+        return self.apply(loss, params)
+
+    def backward(self, loss):
         assert len(loss.shape) == 0 or (len(loss.shape) == 1 and loss.shape[0] == 1), (self._name, loss.shape)
-        metrics = {f"{self._name}_loss": loss.detach()}
-        groups = self.store.groups_of(params)
         loss.backward()
+
+    def apply(self, loss, params):
+        """grad-norm / clip / weight decay / Adam on the groups of `params` (the backward has already run)"""
+        metrics = {f"{self._name}_loss": loss.detach()}
+        groups = self.store.groups_of(list(params))
         norm = self.store.step(groups, self._lr, self._eps, self._clip, self._wd, self.allreduce)
         if self._clip:
             metrics[f"{self._name}_grad_norm"] = norm
         return metrics
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device):
+    """second CUDA stream per device: independent kernel chains (connector vs world-model backward, critic vs actor backward)
+    are enqueued there so their latency-bound small kernels fill the SMs the other chain leaves idle"""
+    k = str(device)
+    s = _SIDE_STREAMS.get(k)
+    if s is None:
+        s = _SIDE_STREAMS[k] = torch.cuda.Stream(device=device)
+    return s
 
 
 class StreamNorm:

@@ -321,6 +321,155 @@ __global__ void __launch_bounds__(THREADS) cat_sample_bwd_kernel(const float* __
   }
 }
 
+
+// ---- thread-per-latent fast paths for K == 32 (the GenRL latent): the 32 class values live in one thread's registers, so
+//      there are no warp reductions at all and one Philox call yields 4 noise values ---------------------------------------
+constexpr int CK = 32;
+__device__ __forceinline__ void cat_probs_thr(const float* __restrict__ lg, float (&p)[CK], float (&pi)[CK], float& usum) {
+#pragma unroll
+  for (int i = 0; i < CK / 4; ++i) { float4 v = reinterpret_cast<const float4*>(lg)[i]; p[4 * i] = v.x; p[4 * i + 1] = v.y; p[4 * i + 2] = v.z; p[4 * i + 3] = v.w; }
+  float mx = p[0];
+#pragma unroll
+  for (int k = 1; k < CK; ++k) mx = fmaxf(mx, p[k]);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CK; ++k) { p[k] = expf(p[k] - mx); s += p[k]; }
+  float us = 0.f;
+#pragma unroll
+  for (int k = 0; k < CK; ++k) { p[k] = p[k] / s; pi[k] = 0.99f * p[k] + 0.01f / CK; us += pi[k]; }
+  usum = us;
+#pragma unroll
+  for (int k = 0; k < CK; ++k) pi[k] = pi[k] / us;
+}
+__device__ __forceinline__ void cat_probs_bwd_thr(const float (&p)[CK], const float (&pi)[CK], float usum, const float (&dpi)[CK], float (&dl)[CK]) {
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < CK; ++k) dot += dpi[k] * pi[k];
+  float dot2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < CK; ++k) { dl[k] = 0.99f * (dpi[k] - dot) / usum; dot2 += dl[k] * p[k]; }
+#pragma unroll
+  for (int k = 0; k < CK; ++k) dl[k] = p[k] * (dl[k] - dot2);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) cat_sample_fwd_thr_kernel(const float* __restrict__ logit, const float* __restrict__ noise,
+                                                                 unsigned long long seed, unsigned long long offset,
+                                                                 const unsigned long long* __restrict__ step_dev, int sample,
+                                                                 T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
+                                                                 long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S) {
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (g >= rows * S) return;
+  if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;
+  float p[CK], pi[CK], usum;
+  cat_probs_thr(logit + g * CK, p, pi, usum);
+  float best = -INFINITY; int bi = 0;
+  if (sample) {
+#pragma unroll
+    for (int j = 0; j < CK / 4; ++j) {
+      float q[4];
+      if (noise) { float4 v = reinterpret_cast<const float4*>(noise + g * CK)[j]; q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+      else {
+        const unsigned long long c = (unsigned long long)g * (CK / 4) + j;
+        uint4 r = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        q[0] = -logf(u32_to_unit_open(r.x)); q[1] = -logf(u32_to_unit_open(r.y)); q[2] = -logf(u32_to_unit_open(r.z)); q[3] = -logf(u32_to_unit_open(r.w));
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { float sc = pi[4 * j + e] / q[e]; if (sc > best) { best = sc; bi = 4 * j + e; } }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < CK; ++k) { float sc = logf(pi[k]); if (sc > best) { best = sc; bi = k; } }
+  }
+  const long long row = g / S; const int sidx = (int)(g % S);
+  float oh[CK];
+#pragma unroll
+  for (int k = 0; k < CK; ++k) oh[k] = k == bi ? 1.f : 0.f;
+  if (stoch32) {
+    float4* o = reinterpret_cast<float4*>(stoch32 + row * ld_stoch32 + sidx * CK);
+#pragma unroll
+    for (int i = 0; i < CK / 4; ++i) o[i] = make_float4(oh[4 * i], oh[4 * i + 1], oh[4 * i + 2], oh[4 * i + 3]);
+  }
+  if (stoch) {
+#pragma unroll
+    for (int i = 0; i < CK / 8; ++i) { float v8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v8[e] = oh[8 * i + e];
+      V8<T>::store(stoch + row * ld_stoch + sidx * CK + 8 * i, v8); }
+  }
+  if (idx_out) idx_out[g] = bi;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) cat_sample_bwd_thr_kernel(const float* __restrict__ logit, const T* __restrict__ dstoch, long long ld_ds,
+                                                                 int sample, float* __restrict__ dlogit, int accumulate, long long rows, int S) {
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (g >= rows * S) return;
+  float p[CK], pi[CK], usum, dpi[CK], dl[CK];
+  cat_probs_thr(logit + g * CK, p, pi, usum);
+  const long long row = g / S; const int sidx = (int)(g % S);
+#pragma unroll
+  for (int i = 0; i < CK / 8; ++i) { float v8[8]; V8<T>::load(dstoch + row * ld_ds + sidx * CK + 8 * i, v8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dpi[8 * i + e] = sample ? v8[e] : v8[e] / pi[8 * i + e]; }
+  cat_probs_bwd_thr(p, pi, usum, dpi, dl);
+  float4* o = reinterpret_cast<float4*>(dlogit + g * CK);
+#pragma unroll
+  for (int i = 0; i < CK / 4; ++i) {
+    float4 v = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+    if (accumulate) { float4 a = o[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    o[i] = v;
+  }
+}
+
+// S == 32, K == 32: one warp per row, one latent per lane
+__global__ void __launch_bounds__(128) kl_fwd_thr_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, float free_bits,
+                                                         float* __restrict__ value, float* __restrict__ out, long long rows) {
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long row = g >> 5;
+  float kl = 0.f, el = 0.f, er = 0.f;
+  if (row < rows) {
+    float p[CK], P[CK], q[CK], Q[CK], us;
+    cat_probs_thr(lhs + g * CK, p, P, us);
+    cat_probs_thr(rhs + g * CK, q, Q, us);
+#pragma unroll
+    for (int k = 0; k < CK; ++k) { float lp = logf(P[k]), lq = logf(Q[k]); kl += P[k] * (lp - lq); el -= P[k] * lp; er -= Q[k] * lq; }
+  }
+  kl = warp_sum(kl); el = warp_sum(el); er = warp_sum(er);
+  if ((threadIdx.x & 31) == 0 && row < rows) {
+    value[row] = kl;
+    const float inv = 1.0f / rows;
+    atomicAdd(&out[0], fmaxf(kl, free_bits) * inv); atomicAdd(&out[1], kl * inv); atomicAdd(&out[2], el * inv); atomicAdd(&out[3], er * inv);
+  }
+}
+
+__global__ void __launch_bounds__(128) kl_bwd_thr_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, const float* __restrict__ value,
+                                                         float free_bits, float w_lhs, float w_rhs, const float* __restrict__ gscale,
+                                                         float* __restrict__ dlhs, float* __restrict__ drhs, long long rows) {
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long row = g >> 5;
+  if (row >= rows) return;
+  const float gs = gscale ? *gscale : 1.0f;
+  const float v = value[row];
+  const float gate = v > free_bits ? 1.f : (v == free_bits ? 0.5f : 0.f);
+  const float cl = gs * w_lhs * gate / rows, cr = gs * w_rhs * gate / rows;
+  float p[CK], P[CK], q[CK], Q[CK], usp, usq, d[CK], dl[CK];
+  cat_probs_thr(lhs + g * CK, p, P, usp);
+  cat_probs_thr(rhs + g * CK, q, Q, usq);
+#pragma unroll
+  for (int k = 0; k < CK; ++k) d[k] = cl * (logf(P[k]) - logf(Q[k]) + 1.0f);
+  cat_probs_bwd_thr(p, P, usp, d, dl);
+  float4* o = reinterpret_cast<float4*>(dlhs + g * CK);
+#pragma unroll
+  for (int i = 0; i < CK / 4; ++i) o[i] = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+#pragma unroll
+  for (int k = 0; k < CK; ++k) d[k] = -cr * P[k] / Q[k];
+  cat_probs_bwd_thr(q, Q, usq, d, dl);
+  o = reinterpret_cast<float4*>(drhs + g * CK);
+#pragma unroll
+  for (int i = 0; i < CK / 4; ++i) o[i] = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
+}
+
 // =================================================================================================
 // Balanced KL with free bits + entropies   reference: EnsembleRSSM.kl_loss dreamer_utils.py:534-555, dreamer.py:249-250
 //   value[r] = KL(lhs || rhs) summed over S;  loss = mix*mean(max(value,free)) + (1-mix)*mean(max(value,free))
@@ -669,18 +818,19 @@ __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc
 using namespace genrl;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
-static inline bool f32_vec_ok(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static inline int ln_lpr(int D) { int l = 4; while (l * 32 < D) l *= 2; return l; }
+static inline int ln_lpr(int D, int nch) { int l = 1; while (l * 8 * nch < D) l *= 2; return l; }
 
 extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
                                 void* y, long long ldy, float* stats, long long M, int D, int dtype) {
   if (M <= 0) return 0;
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(y, ldy) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-      const int lpr = ln_lpr(D);
+      const int nch = D <= 384 ? 6 : 4;
+      const int lpr = ln_lpr(D, nch);
       const long long rpb = 8 * (32 / lpr);
       const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-      ln_fwd_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
+      if (nch == 6) ln_fwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
+      else ln_fwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
     } else {
       ln_act_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D);
     }
@@ -696,14 +846,16 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   size_t smem = (size_t)3 * D * sizeof(float);
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-      const int lpr = ln_lpr(D);
+      const int nch = D <= 384 ? 6 : 4;
+      const int lpr = ln_lpr(D, nch);
       const long long rpb = 8 * (32 / lpr);
       const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-      ln_bwd_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+      if (nch == 6) ln_bwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+      else ln_bwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
       if (dgamma || dlin_bias) {
-        dim3 g2(ceil_div(M, COL_RC), ceil_div(D, 32));
-        ln_colgrad_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act, dgamma,
-                                                        dbeta, dlin_bias, M, D);
+        dim3 g2(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
+        ln_colgrad_vec_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act,
+                                                            dgamma, dbeta, dlin_bias, M, D);
       }
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -716,8 +868,15 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
 
 extern "C" int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype) {
   if (M <= 0) return 0;
-  dim3 grid(ceil_div(M, COL_RC), ceil_div(D, 32));
-  DISPATCH_T(dtype, (colsum_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D)));
+  DISPATCH_T(dtype, {
+    if (D % 8 == 0 && vec_ok<T>(x, ldx)) {
+      dim3 grid(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
+      colsum_vec_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D);
+    } else {
+      dim3 grid(ceil_div(M, COL_RC), ceil_div(D, 32));
+      colsum_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D);
+    }
+  });
   return check_launch("colsum");
 }
 
@@ -760,6 +919,16 @@ extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const floa
                                     int S, int K, int dtype) {
   if (rows <= 0) return 0;
   GENRL_REQUIRE(K <= 32 * KPL, "cat_sample: K=%d > %d unsupported", K, 32 * KPL);
+  const bool fast_ok = K == CK && f32_vec_ok(logit) && (!noise || f32_vec_ok(noise)) && (!stoch32 || vec_ok<float>(stoch32, ld_stoch32));
+  if (fast_ok) {
+    DISPATCH_T(dtype, {
+      if (!stoch || vec_ok<T>(stoch, ld_stoch)) {
+        cat_sample_fwd_thr_kernel<T><<<ceil_div(rows * S, 128), 128, 0, ST(stream)>>>(logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
+                                                                                     stoch32, ld_stoch32, idx, rows, S);
+        return check_launch("cat_sample_fwd");
+      }
+    });
+  }
   DISPATCH_T(dtype, (cat_sample_fwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
                                                                                                      stoch32, ld_stoch32, idx, rows, S, K)));
   return check_launch("cat_sample_fwd");
@@ -769,6 +938,14 @@ extern "C" int genrl_cat_sample_bwd(void* stream, const float* logit, const void
                                     long long rows, int S, int K, int dtype) {
   if (rows <= 0) return 0;
   GENRL_REQUIRE(K <= 32 * KPL, "cat_sample: K=%d > %d unsupported", K, 32 * KPL);
+  if (K == CK && f32_vec_ok(logit) && f32_vec_ok(dlogit)) {
+    DISPATCH_T(dtype, {
+      if (vec_ok<T>(dstoch, ld_ds)) {
+        cat_sample_bwd_thr_kernel<T><<<ceil_div(rows * S, 128), 128, 0, ST(stream)>>>(logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S);
+        return check_launch("cat_sample_bwd");
+      }
+    });
+  }
   DISPATCH_T(dtype, (cat_sample_bwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S, K)));
   return check_launch("cat_sample_bwd");
 }
@@ -777,6 +954,10 @@ extern "C" int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, fl
   if (rows <= 0) return 0;
   GENRL_REQUIRE(K <= 32 * KPL, "kl: K=%d unsupported", K);
   cudaMemsetAsync(out4, 0, 4 * sizeof(float), ST(stream));
+  if (S == 32 && K == CK && f32_vec_ok(lhs) && f32_vec_ok(rhs)) {
+    kl_fwd_thr_kernel<<<ceil_div(rows * 32, 128), 128, 0, ST(stream)>>>(lhs, rhs, free_bits, value, out4, rows);
+    return check_launch("kl_fwd");
+  }
   kl_fwd_kernel<<<row_grid(rows, 148 * 4), THREADS, 0, ST(stream)>>>(lhs, rhs, free_bits, value, out4, rows, S, K);
   return check_launch("kl_fwd");
 }
@@ -784,6 +965,10 @@ extern "C" int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, fl
 extern "C" int genrl_kl_bwd(void* stream, const float* lhs, const float* rhs, const float* value, float free_bits, float w_lhs, float w_rhs,
                             const float* gscale, float* dlhs, float* drhs, long long rows, int S, int K) {
   if (rows <= 0) return 0;
+  if (S == 32 && K == CK && f32_vec_ok(lhs) && f32_vec_ok(rhs) && f32_vec_ok(dlhs) && f32_vec_ok(drhs)) {
+    kl_bwd_thr_kernel<<<ceil_div(rows * 32, 128), 128, 0, ST(stream)>>>(lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows);
+    return check_launch("kl_bwd");
+  }
   kl_bwd_kernel<<<row_grid(rows, 148 * 8), THREADS, 0, ST(stream)>>>(lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows, S, K);
   return check_launch("kl_bwd");
 }

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <algorithm>
+#include <cstdlib>
 
 namespace genrl {
 
@@ -427,39 +428,32 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// choose BN and split-K with a small cost model in SM cycles.  At these sizes the kernel is bound by the L2->SM operand feed, not
-// by the tensor pipe: a 128xBN tile moves (128+BN)*128 B per 64-deep k-block for 2*BN cycles of UMMA work, against a chip-wide L2
-// cap of ~6300 B/clk (B300_MICROARCH.md) and ~96 B/clk per SM.  BN <= 128 runs two CTAs per SM, so one CTA's prologue/epilogue
-// (~1500 + 8*BN clk) hides behind the other's main loop.
+// Tile policy, from measurements on B200 (tests/tune_gemm.py, profiles/r01_gemm_by_shape.txt, ncu --set full in profiles/):
+// at the sizes of this path the kernel is bound by operand-feed LATENCY (a 16..38-deep K loop fed from L2/HBM), not by the tensor
+// pipe or by bandwidth, so what matters is bytes in flight per SM: 128x128 tiles with two co-resident CTAs per SM (2 x 3 stages,
+// and one CTA's prologue/epilogue hidden behind the other's main loop) beat wider single-CTA tiles by 2-3x on cold operands.
+// Split-K only for few-tile / very deep-K problems (conv wgrads), keeping >= 32 k-blocks per split.
 static void choose_tiling(int M, int N, int K, bool allow_split, bool b_mn, int* bn_out, int* splits_out) {
+  (void)b_mn;
   const int sms = num_sms();
-  const int cands[5] = {64, 128, 160, 192, 256};
-  const int mt = ceil_div(M, TC_BM);
+  const int bn = N <= 64 ? 64 : 128;
   const int num_kb = ceil_div(K, TC_BK);
-  double best = 1e30;
-  int best_bn = 128, best_s = 1;
-  for (int ci = 0; ci < 5; ++ci) {
-    const int bn = cands[ci];
-    if (b_mn && (bn % 64) != 0) continue;
-    if (bn > 64 && bn - 64 >= N) continue;              // needlessly wide
-    const int nt = ceil_div(N, bn);
-    for (int s = 1; s <= 512; s *= 2) {
-      if (s > 1 && (!allow_split || num_kb / s < 4)) break;
-      const long long tiles = (long long)mt * nt * s;
-      const long long per_sm = (tiles + sms - 1) / sms;
-      const int kb = ceil_div(num_kb, s);
-      const double bytes_cta = (double)kb * (128.0 + bn) * 128.0;
-      const double mma = (double)per_sm * kb * 2.0 * bn;
-      const double mem = std::max((double)tiles * bytes_cta / 6300.0, (double)per_sm * bytes_cta / 96.0);
-      const double ovh = (1500.0 + 8.0 * bn) * (bn <= 128 ? (double)((per_sm + 1) / 2) : (double)per_sm);
-      const double atom = s > 1 ? 6.0 * bn * per_sm : 0.0;                       // atomic epilogue
-      const double cost = std::max(mma, mem) + ovh + atom;
-      if (cost < best) { best = cost; best_bn = bn; best_s = s; }
-      if (tiles >= 4 * sms) break;
-    }
+  const long long tiles = (long long)ceil_div(M, TC_BM) * ceil_div(N, bn);
+  int sp = 1;
+  if (allow_split) {
+    while ((long long)sp * 2 * tiles <= 2LL * sms && sp < 512) sp *= 2;
+    while (sp > 1 && num_kb / sp < 32) sp /= 2;
   }
+  int best_bn = bn, best_s = sp;
   *bn_out = best_bn;
   *splits_out = best_s;
+  // tuning hook (tests/tune_gemm.py): GENRL_GEMM_BN / GENRL_GEMM_SPLITS force a configuration
+  static const char* fb = getenv("GENRL_GEMM_FORCE");
+  if (fb) {
+    const char* e1 = getenv("GENRL_GEMM_BN"); const char* e2 = getenv("GENRL_GEMM_SPLITS");
+    if (e1 && atoi(e1) > 0) { int v = atoi(e1); if (!(b_mn && (v % 64))) *bn_out = v; }
+    if (e2 && atoi(e2) > 0 && allow_split) *splits_out = std::min(atoi(e2), num_kb);
+  }
 }
 
 }  // namespace genrl

@@ -40,15 +40,18 @@ template <typename T> inline bool vec_ok(const void* p, long long ld) {
   return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % a) == 0;
 }
 
+static inline bool f32_vec_ok(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 __device__ __forceinline__ float group_sum(float v, int lpr) {
   for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-constexpr int FAST_NCH = 4;   // chunks (of 8 elements) per lane -> rows up to 32*4*8 = 1024 wide
 
 // ---- LayerNorm (+SiLU) forward: LPR lanes per row, row in registers ------------------------------------------------
-template <typename T>
+// NCH = chunks (of 8 elements) per lane: 4 for wide rows (up to 32*4*8 = 1024), 6 for the narrow conv rows (48..384 channels,
+// 1..8 lanes per row: more rows per warp and more bytes in flight per lane)
+template <typename T, int FAST_NCH>
 __global__ void __launch_bounds__(256) ln_fwd_fast_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, int act, T* __restrict__ y, long long ldy,
                                                           float* __restrict__ stats, long long M, int D, int lpr) {
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) ln_fwd_fast_kernel(const T* __restrict__ 
 }
 
 // ---- LayerNorm (+SiLU) backward, row pass: dx only ------------------------------------------------------------------
-template <typename T>
+template <typename T, int FAST_NCH>
 __global__ void __launch_bounds__(256) ln_bwd_fast_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
@@ -209,6 +212,86 @@ __global__ void __launch_bounds__(256) colsum_fast_kernel(const T* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 8; ++k) s += red[k][tx];
     atomicAdd(&out[c], s);
+  }
+}
+
+
+// vectorised column pass: a block covers 128 rows x 128 columns, a thread 8 rows x 8 adjacent columns (16-byte loads)
+constexpr int COLV_ROWS = 128;
+template <typename T>
+__global__ void __launch_bounds__(256) ln_colgrad_vec_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
+                                                             const T* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, const float* __restrict__ stats, int act,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlb, long long M, int D) {
+  __shared__ float red[3][16][129];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c = blockIdx.y * 128 + tx * 8;
+  const long long r0 = (long long)blockIdx.x * COLV_ROWS, r1 = min(M, r0 + COLV_ROWS);
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; }
+  if (c < D) {
+    float g[8], b[8];
+    ldf8(gamma + c, g); ldf8(beta + c, b);
+#pragma unroll 2
+    for (long long r = r0 + ty; r < r1; r += 16) {
+      if (dgamma) {
+        float xv[8], dv[8];
+        V8<T>::load(x + r * ldx + c, xv); V8<T>::load(dy + r * lddy + c, dv);
+        const float mean = stats[r * 2], rstd = stats[r * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float h = (xv[j] - mean) * rstd;
+          float gg = dv[j];
+          if (act == GENRL_ACT_SILU) gg *= silu_grad_t<(sizeof(T) == 2)>(h * g[j] + b[j]);
+          a0[j] += gg * h; a1[j] += gg;
+        }
+      }
+      if (dlb) { float v[8]; V8<T>::load(dx + r * lddx + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a2[j] += v[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[0][ty][tx * 8 + j] = a0[j]; red[1][ty][tx * 8 + j] = a1[j]; red[2][ty][tx * 8 + j] = a2[j]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 128; i += 256) {
+    const int a = i >> 7, cc = i & 127, col = blockIdx.y * 128 + cc;
+    if (col >= D) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += red[a][k][cc];
+    if (a == 0 && dgamma) atomicAdd(&dgamma[col], sum);
+    if (a == 1 && dgamma) atomicAdd(&dbeta[col], sum);
+    if (a == 2 && dlb) atomicAdd(&dlb[col], sum);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, long long M, int D) {
+  __shared__ float red[16][129];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int c = blockIdx.y * 128 + tx * 8;
+  const long long r0 = (long long)blockIdx.x * COLV_ROWS, r1 = min(M, r0 + COLV_ROWS);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (c < D) {
+#pragma unroll 2
+    for (long long r = r0 + ty; r < r1; r += 16) { float v[8]; V8<T>::load(x + r * ldx + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += v[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = a[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128; i += 256) {
+    const int col = blockIdx.y * 128 + i;
+    if (col >= D) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sum += red[k][i];
+    atomicAdd(&out[col], sum);
   }
 }
 

@@ -76,7 +76,8 @@ class GraphedCall:
             torch.cuda.current_stream().wait_stream(s)
             return out
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             out = self.fn(*sargs)
         self.graph = g
         self.static_out = out

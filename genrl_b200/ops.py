@@ -790,7 +790,8 @@ _WS = {}
 
 
 def _scan_workspace(B, T, D, device):
-    key = (B, T, D, str(device))
+    # one workspace per stream: the world-model and connector scans may run concurrently on two streams
+    key = (B, T, D, str(device), _st())
     ws = _WS.get(key)
     if ws is None:
         nbytes = lib.load().genrl_rssm_scan_workspace_bytes(B, T, D)

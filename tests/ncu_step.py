@@ -18,7 +18,18 @@ def step(i):
     agent.update_acting_behavior(state, outputs, metrics, data)
 for i in range(2): step(i)
 torch.cuda.synchronize()
+from genrl_b200._lib import lib
+import json
+_orig = lib.genrl_gemm
+shapes = []
+def _logged(*a):
+    shapes.append([a[1], a[2], a[3], a[6], a[9], a[13], a[15]])     # M N K transA transW c_dtype accumulate
+    return _orig(*a)
+lib.__dict__["genrl_gemm"] = _logged
 torch.cuda.profiler.start()
 step(2)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(shapes, open("gpurun_out/gemm_shapes.json", "w"))
