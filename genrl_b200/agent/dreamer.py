@@ -390,15 +390,20 @@ class WorldModel(Module):
         policy_dist = policy(start["feat"])
         start["action"] = torch.zeros_like(policy_dist.sample())
         seq = {k: [v] for k, v in start.items()}
+        ents = []
         for _ in range(horizon):
             inp = seq["feat"][-1]
             policy_dist = policy(stop_gradient(inp))
             action = policy_dist.sample() if not eval_policy else policy_dist.mean
+            if not eval_policy and hasattr(policy_dist, "entropy"):
+                ents.append(policy_dist.entropy())          # same inputs/weights as actor_loss's re-forward (dreamer.py:397)
             state = self.rssm.img_step({k: v[-1] for k, v in seq.items()}, action)
             feat = self.rssm.get_feat(state)
             for key, value in {**state, "action": action, "feat": feat}.items():
                 seq[key].append(value)
         seq = {k: torch.stack(v, 0) for k, v in seq.items()}
+        if len(ents) == horizon and horizon > 0:
+            seq["policy_ent"] = torch.stack(ents, 0)            # [H, N]: entropy of pi(. | sg feat_t), t = 0..H-1
         disc = torch.ones(list(seq["feat"].shape[:-1]) + [1], device=seq["feat"].device)
         seq["discount"] = disc * self.cfg.discount
         seq["weight"] = torch.cumprod(torch.cat([torch.ones_like(disc[:1]), disc[:-1]], 0), 0)
@@ -472,7 +477,7 @@ class ActorCritic(Module):
             # critic forward+backward (large 36 000-row kernels) on a second stream beside the actor's backward through the rollout
             main = torch.cuda.current_stream()
             side = common.side_stream(self.device)
-            with common.RequiresGrad(self.actor), common.RequiresGrad(self.critic):
+            with common.RequiresGrad(self.actor), common.RequiresGrad(self.critic), ops.defer_param_grads(self.actor.parameters()) as dg:
                 seq = world_model.imagine(self.actor, start, is_terminal, hor)
                 reward = reward_fn(seq)
                 seq["reward"], mets1 = self.rewnorm(reward)
@@ -485,18 +490,21 @@ class ActorCritic(Module):
                     critic_loss, mets4 = self.critic_loss(seq_d, target)
                     self.critic_opt.backward(critic_loss)
                 self.actor_opt.backward(actor_loss)
+                dg.flush()
                 main.wait_stream(side)
                 metrics.update(self.actor_opt.apply(actor_loss, self.actor.parameters()))
                 metrics.update(self.critic_opt.apply(critic_loss, self.critic.parameters()))
         else:
-            with common.RequiresGrad(self.actor):
+            with common.RequiresGrad(self.actor), ops.defer_param_grads(self.actor.parameters()) as dg:
                 seq = world_model.imagine(self.actor, start, is_terminal, hor)
                 reward = reward_fn(seq)
                 seq["reward"], mets1 = self.rewnorm(reward)
                 mets1 = {f"reward_{k}": v for k, v in mets1.items()}
                 target, mets2, baseline = self.target(seq)
                 actor_loss, mets3 = self.actor_loss(seq, target, baseline)
-                metrics.update(self.actor_opt(actor_loss, self.actor.parameters()))
+                self.actor_opt.backward(actor_loss)
+                dg.flush()
+                metrics.update(self.actor_opt.apply(actor_loss, self.actor.parameters()))
             with common.RequiresGrad(self.critic):
                 seq = {k: stop_gradient(v) for k, v in seq.items()}
                 critic_loss, mets4 = self.critic_loss(seq, target)
@@ -517,7 +525,12 @@ class ActorCritic(Module):
 
     def actor_loss(self, seq, target, baseline):
         """reference dreamer.py:392-429 (actor_grad == 'dynamics')"""
-        policy = self.actor(stop_gradient(seq["feat"][:-2]))
+        # The reference re-runs the actor on sg(feat[:-2]) only to read its entropy (dreamer.py:397,418); the rollout already
+        # evaluated the same policy on the same inputs, so its entropies (values and gradients) are reused.
+        if "policy_ent" in seq and seq["policy_ent"].shape[0] == seq["feat"].shape[0] - 1:
+            ent_all = seq["policy_ent"][:-1]
+        else:
+            ent_all = self.actor(stop_gradient(seq["feat"][:-2])).entropy()
         metrics = {}
         offset, scale = self.reward_ema(target)
         normed_target = (target - offset) / scale
@@ -527,7 +540,7 @@ class ActorCritic(Module):
         metrics["reward_ema_005"] = self.ema_vals[0]
         metrics["reward_ema_095"] = self.ema_vals[1]
         objective = normed_target[1:]
-        ent = policy.entropy()[:, :, None]
+        ent = ent_all[:, :, None]
         ent_scale = self.cfg.actor_ent
         if ent_scale:
             objective = objective + ent_scale * ent

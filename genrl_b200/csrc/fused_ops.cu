@@ -866,6 +866,25 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   return check_launch("ln_act_bwd");
 }
 
+// column pass alone (deferred parameter gradients: one launch over the rows of all imagination steps)
+extern "C" int genrl_ln_colgrad(void* stream, const void* dy, long long lddy, const void* x, long long ldx, const void* dx, long long lddx,
+                                const float* gamma, const float* beta, const float* stats, int act, float* dgamma, float* dbeta, float* dlin_bias,
+                                long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  DISPATCH_T(dtype, {
+    if (D % 8 == 0 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+      dim3 g2(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
+      ln_colgrad_vec_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act,
+                                                          dgamma, dbeta, dlin_bias, M, D);
+    } else {
+      dim3 g2(ceil_div(M, COL_RC), ceil_div(D, 32));
+      ln_colgrad_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act, dgamma,
+                                                      dbeta, dlin_bias, M, D);
+    }
+  });
+  return check_launch("ln_colgrad");
+}
+
 extern "C" int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype) {
   if (M <= 0) return 0;
   DISPATCH_T(dtype, {

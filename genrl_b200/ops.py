@@ -203,6 +203,77 @@ def mean_of(x, scale=1.0, out=None, accumulate=False):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# deferred parameter gradients: a module applied at every step of a rollout (the actor: H+1 calls on N rows) gets ONE
+# wgrad GEMM / column pass over all H*N rows at the end of the backward instead of H small ones
+# ---------------------------------------------------------------------------------------------------------------
+class DeferredGrads:
+    def __init__(self, params):
+        self.ids = {id(p) for p in params}
+        self.jobs = {}
+
+    def wants(self, w):
+        return id(w) in self.ids
+
+    def add(self, w, b, dy, x, ln=None):
+        j = self.jobs.get(id(w))
+        if j is None:
+            j = self.jobs[id(w)] = dict(w=w, b=b, dy=[], x=[], ln=None, pre=[], stats=[], dlin=[])
+        j["x"].append(x)
+        if ln is None:
+            j["dy"].append(dy)
+        else:
+            gamma, beta, act, pre, stats, dpre = ln
+            j["ln"] = (gamma, beta, act)
+            j["dy"].append(dy); j["pre"].append(pre); j["stats"].append(stats); j["dlin"].append(dpre)
+
+    def flush(self):
+        st = _st()
+        for j in self.jobs.values():
+            w, b = j["w"], j["b"]
+            cat = lambda lst: lst[0] if len(lst) == 1 else torch.cat(lst, 0)
+            X = cat(j["x"])
+            if j["ln"] is None:
+                DY = cat(j["dy"])
+                gbuf, _ = _grad_buf(w)
+                gemm(DY, X, out=gbuf.view(w.shape[0], -1), trans_a=True, trans_w=True, accumulate=True)
+                if b is not None:
+                    bbuf, _ = _grad_buf(b)
+                    lib.genrl_colsum(st, _p(DY), _ld(DY), _p(bbuf), DY.shape[0], DY.shape[1], _CODE[DY.dtype])
+            else:
+                gamma, beta, act = j["ln"]
+                DY, PRE, ST, DP = cat(j["dy"]), cat(j["pre"]), cat(j["stats"]), cat(j["dlin"])
+                gbuf, _ = _grad_buf(w)
+                gemm(DP, X, out=gbuf.view(w.shape[0], -1), trans_a=True, trans_w=True, accumulate=True)
+                gb, _ = _grad_buf(gamma)
+                bb, _ = _grad_buf(beta)
+                lb = _grad_buf(b)[0] if b is not None else None
+                lib.genrl_ln_colgrad(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(DP), _ld(DP), _p(gamma), _p(beta), _p(ST), act, _p(gb), _p(bb),
+                                     _p(lb), DP.shape[0], DP.shape[1], _CODE[DP.dtype])
+        self.jobs = {}
+
+
+_DEFER = None
+
+
+@contextlib.contextmanager
+def defer_param_grads(params):
+    """inside the scope, weight/bias/LayerNorm gradients of `params` are accumulated lazily; call .flush() after backward"""
+    global _DEFER
+    old, _DEFER = _DEFER, DeferredGrads(list(params))
+    try:
+        yield _DEFER
+    finally:
+        _DEFER = old
+
+
+def _deferred_for(w):
+    d = _DEFER
+    if d is not None and d.wants(w) and param_info(w) is not None:
+        return d
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Linear (+ LayerNorm + SiLU)
 # ---------------------------------------------------------------------------------------------------------------
 def _wview(t, wcols):
@@ -214,6 +285,11 @@ def _linear_backward(ctx_x, w, b, dy, need_dx, need_dw, bias_done=False, wcols=N
     dx = dwr = dbr = None
     if need_dx:
         dx = gemm(dy, _wview(compute_weight(w), wcols), trans_w=True, out_dtype=ctx_x.dtype)
+    if need_dw and wcols is None and not bias_done:
+        d = _deferred_for(w)
+        if d is not None:
+            d.add(w, b, dy, ctx_x)
+            return dx, None, None
     if need_dw:
         gbuf, dwr = _grad_buf(w)
         gemm(dy, ctx_x, out=_wview(gbuf.view(w.shape[0], -1), wcols), trans_a=True, trans_w=True, accumulate=True)
@@ -301,6 +377,13 @@ class _LinearLnAct(Function):
         dpre = empty_act(M, D, x.device, pre.dtype)
         train = ctx.needs_input_grad[1]
         gb = bb = dg = db = lb = dlb = None
+        d = _deferred_for(ctx.w) if train else None
+        if d is not None:
+            lib.genrl_ln_act_bwd(_st(), _p(dy), _ld(dy), _p(pre), _ld(pre), _p(ctx.gamma), _p(ctx.beta), _p(stats), ctx.act, _p(dpre), _ld(dpre),
+                                 None, None, None, M, D, _CODE[pre.dtype])
+            d.add(ctx.w, ctx.b, dy, x, ln=(ctx.gamma, ctx.beta, ctx.act, pre, stats, dpre))
+            dx = gemm(dpre, compute_weight(ctx.w), trans_w=True, out_dtype=x.dtype) if ctx.needs_input_grad[0] else None
+            return dx, None, None, None, None, None, None
         if train:
             gb, dg = _grad_buf(ctx.gamma)
             bb, db = _grad_buf(ctx.beta)

@@ -33,6 +33,9 @@ int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* ga
 int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, const void* x, long long ldx, const float* gamma, const float* beta,
                      const float* stats, int act, void* dx, long long lddx, float* dgamma, float* dbeta, float* dlin_bias, long long M,
                      int D, int dtype);
+int genrl_ln_colgrad(void* stream, const void* dy, long long lddy, const void* x, long long ldx, const void* dx, long long lddx,
+                     const float* gamma, const float* beta, const float* stats, int act, float* dgamma, float* dbeta, float* dlin_bias,
+                     long long M, int D, int dtype);
 int genrl_colsum(void* stream, const void* x, long long ldx, float* out, long long M, int D, int dtype);
 
 /* GRUCell tail (LayerNorm(3D) + gates): dreamer_utils.py:777-785. */
