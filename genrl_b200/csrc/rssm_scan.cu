@@ -123,7 +123,11 @@ struct ScanFwdParams {
   float* stats;               // [B*T, 2]
   unsigned long long* fx;     // workspace [T][B][2] fixed-point (sum, sum of squares), zeroed by the host
   unsigned* barrier;          // workspace counter, zeroed by the host
+  long long* dbg;             // optional [T][6] globaltimer stamps of block 0 (profiling aid), or null
 };
+
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SCAN_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[t * 6 + (i)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdParams p) {
   extern __shared__ float smem[];
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
   const int ngroups = (B + SCAN_RB - 1) / SCAN_RB;
   for (int t = 0; t < T; ++t) {
     // ---- phase 1: zh = W_h (m * h_{t-1}) for every batch row ----
+    SCAN_STAMP(0);
     for (int g = warp; g < ngroups; g += SCAN_WARPS) {
       const float* hrow[SCAN_RB];
       float scale[SCAN_RB];
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
     }
     __syncthreads();
     // ---- phase 2: LayerNorm partial sums of this CTA's 24 values per row ----
+    SCAN_STAMP(1);
     unsigned long long* fx = p.fx + (size_t)t * B * 2;
     for (int b = tid; b < B; b += SCAN_THREADS) {
       float s1 = 0.f, s2 = 0.f;
@@ -200,7 +206,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
       fx_add(fx + b * 2, s1, FX_FWD);
       fx_add(fx + b * 2 + 1, s2, FX_FWD);
     }
+    SCAN_STAMP(2);
     grid_barrier(p.barrier, epoch, G);
+    SCAN_STAMP(3);
     // ---- phase 3: full-row statistics ----
     for (int b = tid; b < B; b += SCAN_THREADS) {
       float mean = fx_get(fx + b * 2, 1.0 / FX_FWD) / D3;
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
     }
     __syncthreads();
     // ---- phase 4: gates for the owned units ----
+    SCAN_STAMP(4);
     for (int i = tid; i < B * SCAN_U; i += SCAN_THREADS) {
       int b = i / SCAN_U, u = i % SCAN_U, j = j0 + u;
       float mean = st[b * 2], rstd = st[b * 2 + 1];
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdP
         st_any(p.hprev_t, p.t_dtype, (n + 1) * p.ld_hp + j, hn * m1);
       }
     }
+    SCAN_STAMP(5);
     grid_barrier(p.barrier, epoch, G);
   }
 }
@@ -369,6 +379,10 @@ extern "C" long long genrl_rssm_scan_workspace_bytes(int B, int T, int D) {
   return 256 + (long long)T * B * 2 * 8 + (long long)2 * B * 3 * D * 4;
 }
 
+static long long* g_scan_dbg = nullptr;
+// profiling aid: when set, block 0 of the forward scan records 6 globaltimer stamps per step into dbg[T][6]
+extern "C" int genrl_rssm_scan_set_debug(long long* dbg) { g_scan_dbg = dbg; return 0; }
+
 static int scan_check(int B, int T, int D, const char* who) {
   GENRL_REQUIRE(B > 0 && T > 0, "%s: empty batch", who);
   GENRL_REQUIRE(D % 32 == 0, "%s: deter size %d must be a multiple of 32", who, D);
@@ -390,6 +404,7 @@ extern "C" int genrl_rssm_scan_fwd(void* stream, int B, int T, int D, const floa
   p.gx = gx; p.Wh = Wh; p.ldw = ldw; p.gamma = gamma; p.beta = beta; p.mask = mask; p.h0 = h0;
   p.deter = deter; p.deter_t = deter_t; p.ld_dt = ld_dt; p.t_dtype = t_dtype; p.hprev_t = hprev_t; p.ld_hp = ld_hp;
   p.z = z; p.stats = stats;
+  p.dbg = g_scan_dbg;
   p.barrier = reinterpret_cast<unsigned*>(workspace);
   p.fx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(workspace) + 256);
   size_t smem = ((size_t)3 * SCAN_U * D + (size_t)B * 3 * SCAN_U + (size_t)B * 2) * sizeof(float);

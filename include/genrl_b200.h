@@ -132,6 +132,7 @@ int genrl_actor_objective(void* stream, const float* target, const float* ent, c
 
 /* Persistent time-loop of EnsembleRSSM.observe / VideoSSM.update: dreamer_utils.py:362-371 + :432-473 + :771-785. */
 long long genrl_rssm_scan_workspace_bytes(int B, int T, int D);
+int genrl_rssm_scan_set_debug(long long* dbg);   /* profiling aid: per-phase globaltimer stamps of block 0, dbg[T][6] or NULL */
 int genrl_rssm_scan_fwd(void* stream, int B, int T, int D, const float* gx, const float* Wh, long long ldw, const float* gamma,
                         const float* beta, const float* mask, const float* h0, float* deter, void* deter_t, long long ld_dt, void* hprev_t,
                         long long ld_hp, int t_dtype, float* z, float* stats, void* workspace);
