@@ -369,7 +369,7 @@ def test_adam_step_matches_oracle():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,T,D,Hd,resets", [(3, 5, 64, 64, True), (50, 8, 256, 128, True), (7, 6, 1024, 1024, False)])
+@pytest.mark.parametrize("B,T,D,Hd,resets", [(3, 5, 64, 64, True), (50, 8, 256, 128, True), (7, 6, 1024, 1024, False), (70, 3, 128, 64, True)])
 def test_gru_scan_matches_stepwise(dtype, B, T, D, Hd, resets):
     """persistent scan kernel == T sequential GRU steps (forward values, dgx, dW_h, dgamma, dh0)"""
     with ops.use_dtype(dtype):
@@ -403,7 +403,8 @@ def test_gru_scan_matches_stepwise(dtype, B, T, D, Hd, resets):
         dt = ops.gru_scan(gxd, wd, gd, bd, mask.reshape(-1).to(DEV).contiguous(), h0d, B, T, Hd)
         (dt * dd.to(DEV)).sum().backward()
         tol = dict(rtol=1e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
-        close(dt, deter, rtol=1e-4, atol=2e-5, msg="scan deter")        # the recurrence itself is fp32 in both modes
+        # fp32 mode: FFMA recurrence; bf16 mode (D % 128 == 0): the recurrent product runs on bf16 tensor cores, state stays fp32
+        close(dt, deter, msg="scan deter", **(dict(rtol=1e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)))
         close(gxd.grad, gxr.grad, msg="scan dgx", **tol)
         close(h0d.grad, h0r.grad, msg="scan dh0", **tol)
         close(gd.grad, gr.grad, msg="scan dgamma", **tol)
