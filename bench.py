@@ -101,7 +101,7 @@ def make_cfg(args, device, precision):
 
 
 def synthetic(B, T, A, seed):
-    from oracle.genrl_oracle import synthetic_batch        # data generator only (torch.randint / rand), not the checker
+    from genrl_b200.synthetic import synthetic_batch
     return synthetic_batch(B, T, A, clip_dim=512, seed=seed)
 
 

@@ -113,3 +113,26 @@ def test_data_parallel_host_logic_gloo_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(n == 3 for _, _, n in res)
+
+
+def test_product_synthetic_batches_equal_the_test_side_generator():
+    from genrl_b200.synthetic import synthetic_batch
+    from oracle.genrl_oracle import synthetic_batch as oracle_batch
+    a, b = synthetic_batch(3, 8, 5, clip_dim=16, seed=4, resets=0.2), oracle_batch(3, 8, 5, clip_dim=16, seed=4, resets=0.2)
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under genrl_b200/ may import it, and bench.py only in its CPU-baseline legs"""
+    import re
+    pkg = os.path.join(ROOT, "genrl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports oracle/"
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    native = bench[bench.index("def run_native"):bench.index("def roofline_pass")]
+    assert "oracle" not in native.replace("cpu_baseline", "")
