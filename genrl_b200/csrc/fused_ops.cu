@@ -818,6 +818,11 @@ __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc
 using namespace genrl;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
+static int num_sms_rows() {
+  static int n = 0;
+  if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
 static inline int ln_lpr(int D, int nch) { int l = 1; while (l * 8 * nch < D) l *= 2; return l; }
 
 extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
@@ -846,16 +851,30 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   size_t smem = (size_t)3 * D * sizeof(float);
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-      const int nch = D <= 384 ? 6 : 4;
-      const int lpr = ln_lpr(D, nch);
-      const long long rpb = 8 * (32 / lpr);
-      const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-      if (nch == 6) ln_bwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
-      else ln_bwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
       if (dgamma || dlin_bias) {
-        dim3 g2(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
-        ln_colgrad_vec_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act,
-                                                            dgamma, dbeta, dlin_bias, M, D);
+        // one pass: dx and the parameter gradients (narrow rows use 2 chunks per lane: 128 registers, two blocks per SM)
+        const int nch = D <= 384 ? 2 : 4;
+        const int lpr = ln_lpr(D, nch);
+        const long long rpb = 8 * (32 / lpr);
+        static int bps2 = 0, bps4 = 0;
+        int& bps = nch == 2 ? bps2 : bps4;
+        if (bps == 0) {
+          if (nch == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ln_bwd_colg_kernel<T, 2>, 256, 0);
+          else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ln_bwd_colg_kernel<T, 4>, 256, 0);
+          if (bps <= 0) bps = 1;
+        }
+        const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, (long long)num_sms_rows() * bps);
+        if (nch == 2) ln_bwd_colg_kernel<T, 2><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
+                                                                             dgamma, dbeta, dlin_bias, M, D, lpr);
+        else ln_bwd_colg_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
+                                                                    dgamma, dbeta, dlin_bias, M, D, lpr);
+      } else {
+        const int nch = D <= 384 ? 6 : 4;
+        const int lpr = ln_lpr(D, nch);
+        const long long rpb = 8 * (32 / lpr);
+        const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
+        if (nch == 6) ln_bwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+        else ln_bwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
       }
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

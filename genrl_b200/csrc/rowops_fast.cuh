@@ -158,6 +158,99 @@ __global__ void __launch_bounds__(256) ln_bwd_fast_kernel(const T* __restrict__ 
   }
 }
 
+// ---- LayerNorm (+SiLU) backward, row pass + parameter gradients in ONE pass ------------------------------------------
+// Same row mapping as ln_bwd_fast_kernel; every lane additionally keeps the column partials of the columns it owns
+// (dgamma += g*xhat, dbeta += g, dlin_bias += dx) in registers across its grid-stride rows; they are reduced over the rows
+// of a warp by shuffles, over the warps of a block in shared memory, and leave the block as one fp32 atomic per column.
+// Replaces the separate column kernel (a second read of dy, x, dx): traffic 3 tensors instead of 6.
+template <typename T, int FAST_NCH>
+__global__ void __launch_bounds__(256, (FAST_NCH <= 2 ? 2 : 1)) ln_bwd_colg_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlb,
+                                                          long long M, int D, int lpr) {
+  __shared__ float red[3 * 1024];
+  for (int i = threadIdx.x; i < 3 * D; i += 256) red[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane % lpr, rwi = lane / lpr, rpw = 32 / lpr;
+  const long long wstride = (long long)gridDim.x * 8 * rpw;
+  float a0[FAST_NCH][8], a1[FAST_NCH][8], a2[FAST_NCH][8];
+#pragma unroll
+  for (int i = 0; i < FAST_NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[i][j] = 0.f; a1[i][j] = 0.f; a2[i][j] = 0.f; }
+  for (long long base = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw; base < M; base += wstride) {
+    const long long row = base + rwi;
+    const bool valid = row < M;
+    const float mean = valid ? stats[row * 2] : 0.f, rstd = valid ? stats[row * 2 + 1] : 0.f;
+    float gh[FAST_NCH][8], xh[FAST_NCH][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < FAST_NCH; ++i) {
+      const int c = (i * lpr + sub) * 8;
+      if (valid && c < D) {
+        float d[8], g[8], b[8];
+        V8<T>::load(dy + row * lddy + c, d);
+        V8<T>::load(x + row * ldx + c, xh[i]);
+        ldf8(gamma + c, g);
+        if (act == GENRL_ACT_SILU) ldf8(beta + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float h = (xh[i][j] - mean) * rstd;
+          float gg = d[j];
+          if (act == GENRL_ACT_SILU) gg *= silu_grad_t<(sizeof(T) == 2)>(h * g[j] + b[j]);
+          a0[i][j] += gg * h; a1[i][j] += gg;
+          gg *= g[j];
+          xh[i][j] = h; gh[i][j] = gg;
+          s1 += gg; s2 += gg * h;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gh[i][j] = 0.f; xh[i][j] = 0.f; }
+      }
+    }
+    s1 = group_sum(s1, lpr) / D; s2 = group_sum(s2, lpr) / D;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < FAST_NCH; ++i) {
+        const int c = (i * lpr + sub) * 8;
+        if (c < D) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { o[j] = rstd * (gh[i][j] - s1 - xh[i][j] * s2); a2[i][j] += o[j]; }
+          V8<T>::store(dx + row * lddx + c, o);
+        }
+      }
+    }
+  }
+  // rows of one warp -> lanes rwi == 0
+  for (int o = lpr; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < FAST_NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a0[i][j] += __shfl_xor_sync(0xffffffffu, a0[i][j], o);
+        a1[i][j] += __shfl_xor_sync(0xffffffffu, a1[i][j], o);
+        a2[i][j] += __shfl_xor_sync(0xffffffffu, a2[i][j], o);
+      }
+  }
+  if (rwi == 0) {
+#pragma unroll
+    for (int i = 0; i < FAST_NCH; ++i) {
+      const int c = (i * lpr + sub) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&red[c + j], a0[i][j]); atomicAdd(&red[D + c + j], a1[i][j]); atomicAdd(&red[2 * D + c + j], a2[i][j]); }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    if (dgamma) { atomicAdd(&dgamma[c], red[c]); atomicAdd(&dbeta[c], red[D + c]); }
+    if (dlb) atomicAdd(&dlb[c], red[2 * D + c]);
+  }
+}
+
 // ---- column pass of the LayerNorm backward: dgamma/dbeta/dlin_bias += column sums over a chunk of rows --------------
 constexpr int COL_RC = 256;   // rows per block
 template <typename T>

@@ -379,9 +379,12 @@ class _LinearLnAct(Function):
         gb = bb = dg = db = lb = dlb = None
         d = _deferred_for(ctx.w) if train else None
         if d is not None:
+            # LayerNorm / bias gradients come out of the fused row pass now; only the wgrad GEMM is deferred (one GEMM over all steps)
+            gb, bb = _grad_buf(ctx.gamma)[0], _grad_buf(ctx.beta)[0]
+            lb = _grad_buf(ctx.b)[0] if ctx.b is not None else None
             lib.genrl_ln_act_bwd(_st(), _p(dy), _ld(dy), _p(pre), _ld(pre), _p(ctx.gamma), _p(ctx.beta), _p(stats), ctx.act, _p(dpre), _ld(dpre),
-                                 None, None, None, M, D, _CODE[pre.dtype])
-            d.add(ctx.w, ctx.b, dy, x, ln=(ctx.gamma, ctx.beta, ctx.act, pre, stats, dpre))
+                                 _p(gb), _p(bb), _p(lb), M, D, _CODE[pre.dtype])
+            d.add(ctx.w, None, dpre, x)
             dx = gemm(dpre, compute_weight(ctx.w), trans_w=True, out_dtype=x.dtype) if ctx.needs_input_grad[0] else None
             return dx, None, None, None, None, None, None
         if train:
