@@ -1,0 +1,588 @@
+// Implicit-GEMM convolutions on tcgen05 for the Dreamer conv stacks (reference Encoder dreamer_utils.py:580-621: Conv2d k4 s2;
+// Decoder :656-706: ConvTranspose2d k5/k6 s2), NHWC bf16 activations.  No im2col / col2im buffers: the "virtual im2col" tile
+//     col[row, kidx] = in[n, yy*sy + a*ts, xx*sy + b*ts, c]        row = (n, yy, xx),  kidx = ((a*tw + b)*C + c)
+// is gathered straight into the 128B-swizzled shared-memory layout UMMA expects by cp.async (16-byte channel chunks, zero fill
+// outside the image), while the (small) filter matrix arrives by TMA.  One geometry covers every pass of both layer types:
+//   gather form  (sy = 2, ts = +1, taps k x k)       : Conv2d forward, ConvTranspose2d dgrad           -> conv_fwd_kernel
+//   sub-pixel form (sy = 1, ts = -1, taps T x T,     : ConvTranspose2d forward, Conv2d dgrad           -> conv_fwd_kernel
+//      T = ceil(k/2), 4 output parity classes stacked along N: out[n, 2yy+py, 2xx+px, co])
+//   weight gradients (gather form, K = pixels)       : dW[s, kidx] = sum_rows S[row, s] * col[row, kidx] -> conv_wgrad_kernel
+// Warp roles: warp 0 = TMA (filters / S matrix), warp 1 = TMEM allocator + MMA issuer, warps 2..5 = cp.async gather producers
+// during the main loop, then the epilogue (tcgen05.ld -> bias -> NHWC bf16 or NCHW fp32 stores / fp32 atomics for split-K wgrad).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <algorithm>
+
+namespace genrl {
+
+constexpr int CV_BM = 128;
+constexpr int CV_BK = 64;
+constexpr int CV_THREADS = 192;
+constexpr int CV_GATHER = 128;     // gather threads (warps 2..5)
+constexpr int CV_LAG = 2;          // cp.async groups kept in flight per gather thread before the stage is published
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct ConvGeom {
+  const __nv_bfloat16* in;   // [Nimg, IH, IW, C] NHWC
+  int Nimg, IH, IW, C;
+  int RH, RW;                // row grid per image
+  int sy, ts, tw;            // input stride of the row grid, tap direction (+1/-1), taps along x
+  int K;                     // th*tw*C
+  long long rows;            // Nimg*RH*RW
+};
+
+struct ConvFwdParams {
+  ConvGeom g;
+  int N, Cpad, Cout, ncls;   // N = ncls*Cpad output columns; class = (py, px) of the sub-pixel form
+  int OH, OW;
+  int out_mode;              // 0: NHWC bf16 rows [Nimg*OH*OW, Cout]; 1: NCHW fp32 [Nimg, Cout, OH, OW]
+  void* out;
+  const float* bias;
+  int num_kb;
+};
+
+struct ConvWgParams {
+  ConvGeom g;
+  int Cs;                    // channels of the row-aligned matrix S [rows, Cs]
+  float* dw; int ldw;        // [Cs, K] fp32, accumulated atomically
+  int num_kb, kb_per_split;  // k-blocks of 64 rows
+};
+
+// publish cp.async-filled stages: the writes of one group are complete for this thread after wait_group, become visible to the
+// tensor-core (async) proxy after the proxy fence, then the thread arrives on the stage's full barrier
+__device__ __forceinline__ void publish_stage(uint64_t* bar) {
+  fence_proxy_async();
+  mbar_arrive(bar);
+}
+
+// =================================================================================================
+// forward-type kernel: D[row, col] = sum_k col[row, k] * Wm[col, k]
+// =================================================================================================
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, (BN <= 96 ? 2 : 1))
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = CV_BM * CV_BK * 2;
+  constexpr int B_BYTES = BN * CV_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long m0 = (long long)blockIdx.x * CV_BM;
+  const int n0 = blockIdx.y * BN;
+  const int nkb = p.num_kb;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], CV_GATHER + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], B_BYTES);
+        tma_load_2d(&tmW, &full_bar[stage], smem + stage * STAGE_BYTES + A_BYTES, kb * CV_BK, n0);     // box {64 k, BN n}
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < CV_BK / 16; ++k)
+          umma_bf16(tmem_base, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ gather producers ------------------------------
+    const ConvGeom& g = p.g;
+    const int t = threadIdx.x - 64;
+    const int j = t & 7;                     // 16-byte chunk of the 64-wide k block
+    const int rg = t >> 3;                   // rows rg + 16*i
+    const __nv_bfloat16* img[8];
+    int yx0[8];
+    const int rhw = g.RH * g.RW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long row = m0 + rg + 16 * i;
+      if (row < g.rows) {
+        const long long n = row / rhw;
+        const int rem = (int)(row - n * rhw);
+        const int yy = rem / g.RW, xx = rem - yy * g.RW;
+        img[i] = g.in + n * ((long long)g.IH * g.IW * g.C);
+        yx0[i] = ((yy * g.sy + 4096) << 16) | (xx * g.sy + 4096);       // biased so negative tap offsets stay positive
+      } else {
+        img[i] = nullptr;
+        yx0[i] = 0;
+      }
+    }
+    const uint32_t dst_off = (uint32_t)(rg * 128 + ((j ^ (rg & 7)) << 4));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const int kidx = kb * CV_BK + j * 8;
+      const bool kval = kidx < g.K;
+      const int tap = kidx / g.C;
+      const int c = kidx - tap * g.C;
+      const int a = tap / g.tw;
+      const int b = tap - a * g.tw;
+      const int dy = a * g.ts, dx = b * g.ts;
+      const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) + dst_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int iy = (yx0[i] >> 16) - 4096 + dy, ix = (yx0[i] & 0xffff) - 4096 + dx;
+        const bool ok = kval && img[i] != nullptr && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW;
+        const void* src = ok ? (const void*)(img[i] + ((long long)iy * g.IW + ix) * g.C + c) : (const void*)g.in;
+        cp_async16(sa + i * (16 * 128), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (kb >= CV_LAG) {
+        cp_async_wait<CV_LAG>();
+        publish_stage(&full_bar[(kb - CV_LAG) % STAGES]);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (nkb >= 2) { cp_async_wait<1>(); publish_stage(&full_bar[(nkb - 2) % STAGES]); }
+    cp_async_wait<0>();
+    publish_stage(&full_bar[(nkb - 1) % STAGES]);
+
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const long long row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < g.rows;
+    long long n = 0; int yy = 0, xx = 0;
+    if (row_ok) { n = row / rhw; const int rem = (int)(row - n * rhw); yy = rem / g.RW; xx = rem - yy * g.RW; }
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 32) {
+      if (n0 + cc >= p.N) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = n0 + cc + 16 * h;
+        if (col >= p.N || cc + 16 * h >= BN) continue;
+        const int cls = col / p.Cpad;
+        const int co0 = col - cls * p.Cpad;
+        const int nco = min(16, p.Cout - co0);
+        if (nco <= 0) continue;
+        int oy = yy, ox = xx;
+        if (p.ncls > 1) { oy = 2 * yy + (cls >> 1); ox = 2 * xx + (cls & 1); }
+        if (oy >= p.OH || ox >= p.OW) continue;
+        float f[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[16 * h + q]) + ((p.bias != nullptr && q < nco) ? __ldg(p.bias + co0 + q) : 0.f);
+        if (p.out_mode == 0) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((n * p.OH + oy) * p.OW + ox) * p.Cout + co0;
+          if (nco == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; q += 8) {
+              uint4 pk;
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(f[q], f[q + 1]), a1 = __floats2bfloat162_rn(f[q + 2], f[q + 3]);
+              __nv_bfloat162 a2 = __floats2bfloat162_rn(f[q + 4], f[q + 5]), a3 = __floats2bfloat162_rn(f[q + 6], f[q + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              *reinterpret_cast<uint4*>(o + q) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) if (q < nco) o[q] = __float2bfloat16_rn(f[q]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + ((n * p.Cout + co0) * p.OH + oy) * p.OW + ox;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) if (q < nco) o[(long long)q * p.OH * p.OW] = f[q];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// =================================================================================================
+// weight-gradient kernel: dW[s, kidx] += sum_{rows of this split} S[row, s] * col[row, kidx]
+// A = S^T (MN-major, TMA), B = col (MN-major, gathered: 64 pixel rows x BN k-columns per stage)
+// =================================================================================================
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CV_THREADS, 2)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = CV_BM * CV_BK * 2;
+  constexpr int B_BYTES = BN * CV_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int NG = BN / 64;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * CV_BM;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  constexpr int TMEM_COLS = BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmS);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], CV_GATHER + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[stage], A_BYTES);
+#pragma unroll
+        for (int q = 0; q < CV_BM / 64; ++q)                                     // box {64 s-channels, 64 rows}
+          tma_load_2d(&tmS, &full_bar[stage], sa + q * (64 * CV_BK * 2), m0 + 64 * q, kb * CV_BK);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < CV_BK / 16; ++k)
+          umma_bf16(tmem_base, make_smem_desc(sa + k * 2048, 64 * CV_BK * 2, 1024), make_smem_desc(sb + k * 2048, 64 * CV_BK * 2, 1024), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (kb == nkb - 1) umma_commit(tmem_full_bar);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ gather producers ------------------------------
+    const ConvGeom& g = p.g;
+    const int t = threadIdx.x - 64;
+    const int j = t & 7;
+    const int rg = t >> 3;                   // rows rg + 16*i, i < 4
+    long long koff[NG];                      // element offset of this thread's k-chunk relative to the row's base pixel
+    int kdy[NG], kdx[NG];
+    bool kval[NG];
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      const int kidx = n0 + q * 64 + j * 8;
+      kval[q] = kidx < g.K;
+      const int tap = kidx / g.C;
+      const int c = kidx - tap * g.C;
+      const int a = tap / g.tw;
+      const int b = tap - a * g.tw;
+      kdy[q] = a * g.ts; kdx[q] = b * g.ts;
+      koff[q] = ((long long)kdy[q] * g.IW + kdx[q]) * g.C + c;
+    }
+    const int rhw = g.RH * g.RW;
+    const uint32_t dst_off = (uint32_t)(rg * 128 + ((j ^ (rg & 7)) << 4));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES + A_BYTES) + dst_off;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = (long long)(kb_begin + kb) * CV_BK + rg + 16 * i;
+        const bool rok = row < g.rows;
+        const long long n = rok ? row / rhw : 0;
+        const int rem = rok ? (int)(row - n * rhw) : 0;
+        const int yy = rem / g.RW, xx = rem - yy * g.RW;
+        const int iy0 = yy * g.sy, ix0 = xx * g.sy;
+        const __nv_bfloat16* base = g.in + ((n * g.IH + iy0) * g.IW + ix0) * g.C;
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+          const bool ok = rok && kval[q] && (unsigned)(iy0 + kdy[q]) < (unsigned)g.IH && (unsigned)(ix0 + kdx[q]) < (unsigned)g.IW;
+          const void* src = ok ? (const void*)(base + koff[q]) : (const void*)g.in;
+          cp_async16(sb + q * 8192 + i * (16 * 128), src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (kb >= CV_LAG) {
+        cp_async_wait<CV_LAG>();
+        publish_stage(&full_bar[(kb - CV_LAG) % STAGES]);
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (nkb >= 2) { cp_async_wait<1>(); publish_stage(&full_bar[(nkb - 2) % STAGES]); }
+    cp_async_wait<0>();
+    publish_stage(&full_bar[(nkb - 1) % STAGES]);
+
+    // ------------------------------ epilogue: fp32 atomics into dW ------------------------------
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + quarter * 32 + lane;
+    const bool m_ok = m < p.Cs;
+#pragma unroll 1
+    for (int cc = 0; cc < BN; cc += 32) {
+      if (n0 + cc >= g.K) break;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
+      if (!m_ok) continue;
+      float* o = p.dw + (long long)m * p.ldw + n0 + cc;
+      const int ncols = min(32, g.K - (n0 + cc));
+#pragma unroll
+      for (int q = 0; q < 32; ++q) if (q < ncols) atomicAdd(o + q, __uint_as_float(v[q]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// =================================================================================================
+// filter packing
+// =================================================================================================
+// sub-pixel form: Wq[(cls*Cpad + b), ((a_*T + b_)*A + a)] = W4[a][b][py + 2a_][px + 2b_]   (0 outside the filter / for b >= B)
+// W4 is [A][B][k][k] fp32: Conv2d weight [Cout][Cin] (A = Cout, used by its dgrad) or ConvTranspose2d weight [Cin][Cout] (A = Cin, forward)
+__global__ void __launch_bounds__(256) conv_pack_parity_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int A, int B, int k, int T,
+                                                               int Cpad) {
+  const long long K = (long long)T * T * A;
+  const long long total = 4LL * Cpad * K;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int a = (int)(i % A);
+    const int tap = (int)((i / A) % (T * T));
+    const long long r = i / K;
+    const int b = (int)(r % Cpad), cls = (int)(r / Cpad);
+    const int ky = (cls >> 1) + 2 * (tap / T), kx = (cls & 1) + 2 * (tap % T);
+    float v = 0.f;
+    if (b < B && ky < k && kx < k) v = w[(((long long)a * B + b) * k + ky) * k + kx];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// gather form with channel padding: Wg[a, (ky*k + kx)*Cp + b] = W4[a][b][ky][kx]  (0 for b >= B)
+__global__ void __launch_bounds__(256) conv_pack_gather_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int A, int B, int k, int Cp) {
+  const long long total = (long long)A * k * k * Cp;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int b = (int)(i % Cp);
+    const int tap = (int)((i / Cp) % (k * k));
+    const long long a = i / ((long long)Cp * k * k);
+    dst[i] = __float2bfloat16_rn(b < B ? w[((a * B + b) * k * k) + tap] : 0.f);
+  }
+}
+
+// grad[a][b][tap] += dwp[a, tap*Cp + b]
+__global__ void __launch_bounds__(256) conv_unpack_wgrad_kernel(const float* __restrict__ dwp, long long ld, float* __restrict__ grad, int A, int B, int kk,
+                                                                int Cp) {
+  const long long total = (long long)A * B * kk;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int tap = (int)(i % kk);
+    const int b = (int)((i / kk) % B);
+    const long long a = i / ((long long)kk * B);
+    grad[i] += dwp[a * ld + (long long)tap * Cp + b];
+  }
+}
+
+// NCHW fp32 [N,C,H,W] -> NHWC bf16 with the channel dimension zero-padded to Cp
+__global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long N, int C, int H, int W,
+                                                               int Cp) {
+  const long long total = N * H * W;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long n = i / ((long long)H * W);
+    const long long hw = i - n * H * W;
+    for (int c = 0; c < Cp; ++c) y[i * Cp + c] = __float2bfloat16_rn(c < C ? x[(n * C + c) * H * W + hw] : 0.f);
+  }
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap& tw, const ConvFwdParams& p, cudaStream_t st) {
+  constexpr int STAGES = BN <= 96 ? 3 : 4;
+  constexpr int SMEM = STAGES * (CV_BM + BN) * CV_BK * 2 + 1024 + 256;
+  static bool attr_set = false;
+  auto kern = conv_fwd_kernel<BN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    GENRL_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_fwd) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((p.g.rows + CV_BM - 1) / CV_BM), (unsigned)ceil_div(p.N, BN), 1);
+  kern<<<grid, CV_THREADS, SMEM, st>>>(tw, p);
+  return check_launch("conv_fwd_kernel");
+}
+
+}  // namespace genrl
+
+using namespace genrl;
+
+static int fill_geom(ConvGeom* g, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int ts, int th, int tw) {
+  GENRL_REQUIRE(C % 8 == 0 && C > 0, "conv_igemm: channels must be a multiple of 8 (got %d)", C);
+  GENRL_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv_igemm: input must be 16-byte aligned");
+  GENRL_REQUIRE(IH < 4096 && IW < 4096 && RH * sy + th < 8192 && RW * sy + tw < 8192, "conv_igemm: image too large");
+  g->in = reinterpret_cast<const __nv_bfloat16*>(in);
+  g->Nimg = Nimg; g->IH = IH; g->IW = IW; g->C = C; g->RH = RH; g->RW = RW; g->sy = sy; g->ts = ts; g->tw = tw;
+  g->K = th * tw * C;
+  g->rows = (long long)Nimg * RH * RW;
+  return 0;
+}
+
+// Forward-type implicit GEMM (see the file header).  in: bf16 NHWC [Nimg,IH,IW,C]; Wm: bf16 [ncls*Cpad, th*tw*C] (ld = ldw);
+// output pixel of (row, class): ncls == 1 -> (yy, xx); ncls == 4 -> (2yy + py, 2xx + px).
+extern "C" int genrl_conv_igemm_fwd(void* stream, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int ts, int th, int tw,
+                                    const void* Wm, long long ldw, int Cpad, int Cout, int ncls, int OH, int OW, void* out, int out_mode,
+                                    const float* bias) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (Nimg <= 0) return 0;
+  ConvFwdParams p;
+  if (fill_geom(&p.g, in, Nimg, IH, IW, C, RH, RW, sy, ts, th, tw)) return 1;
+  GENRL_REQUIRE(ncls == 1 || ncls == 4, "conv_igemm_fwd: ncls must be 1 or 4");
+  GENRL_REQUIRE(Cpad % 16 == 0 && Cout <= Cpad, "conv_igemm_fwd: Cpad must be a multiple of 16 covering Cout");
+  GENRL_REQUIRE(out_mode == 1 || Cout % 8 == 0, "conv_igemm_fwd: NHWC output needs Cout %% 8 == 0");
+  GENRL_REQUIRE((ldw % 8) == 0 && (reinterpret_cast<uintptr_t>(Wm) & 15) == 0, "conv_igemm_fwd: filter matrix must be 16-byte aligned rows");
+  p.N = ncls * Cpad; p.Cpad = Cpad; p.Cout = Cout; p.ncls = ncls; p.OH = OH; p.OW = OW; p.out_mode = out_mode; p.out = out; p.bias = bias;
+  p.num_kb = ceil_div(p.g.K, CV_BK);
+  int bn;
+  if (p.N <= 16) bn = 16;
+  else if (p.N <= 48) bn = 48;
+  else if (p.N <= 64) bn = 64;
+  else if (p.N <= 96) bn = 96;
+  else if (p.N % 192 == 0 || p.N > 128) bn = 192;
+  else bn = 128;
+  CUtensorMap tm;
+  if (make_map(&tm, Wm, ncls == 1 ? Cout : p.N, p.g.K, ldw, 64, bn)) return 1;      // rows past the matrix are zero-filled by TMA
+  switch (bn) {
+    case 16: return launch_fwd<16>(tm, p, st);
+    case 48: return launch_fwd<48>(tm, p, st);
+    case 64: return launch_fwd<64>(tm, p, st);
+    case 96: return launch_fwd<96>(tm, p, st);
+    case 128: return launch_fwd<128>(tm, p, st);
+    default: return launch_fwd<192>(tm, p, st);
+  }
+}
+
+// Weight gradients in gather form: dw[Cs, th*tw*C] (fp32, ld = lddw) += S^T col, S: bf16 [rows, Cs] (ld = lds) aligned with the row grid.
+extern "C" int genrl_conv_igemm_wgrad(void* stream, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int th, int tw,
+                                      const void* S, long long lds, int Cs, float* dw, long long lddw) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (Nimg <= 0) return 0;
+  ConvWgParams p;
+  if (fill_geom(&p.g, in, Nimg, IH, IW, C, RH, RW, sy, 1, th, tw)) return 1;
+  GENRL_REQUIRE((lds % 8) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0, "conv_igemm_wgrad: S must have 16-byte aligned rows");
+  p.Cs = Cs; p.dw = dw; p.ldw = (int)lddw;
+  p.num_kb = ceil_div(p.g.rows, CV_BK);
+  constexpr int BN = 128, STAGES = 3;
+  const int ntiles = ceil_div(p.g.K, BN) * ceil_div(Cs, CV_BM);
+  int sms = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  int splits = std::max(1, (2 * sms) / ntiles);
+  splits = std::min(splits, std::max(1, p.num_kb / 8));
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  CUtensorMap tm;
+  if (make_map(&tm, S, p.g.rows, Cs, lds, 64, 64)) return 1;
+  constexpr int SMEM = STAGES * (CV_BM + BN) * CV_BK * 2 + 1024 + 256;
+  static bool attr_set = false;
+  auto kern = conv_wgrad_kernel<BN, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    GENRL_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_wgrad) failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.g.K, BN), ceil_div(Cs, CV_BM), splits);
+  kern<<<grid, CV_THREADS, SMEM, st>>>(tm, p);
+  return check_launch("conv_wgrad_kernel");
+}
+
+extern "C" int genrl_conv_pack_parity(void* stream, const float* w, void* dst, int A, int B, int k, int Cpad) {
+  const int T = (k + 1) / 2;
+  const long long total = 4LL * Cpad * T * T * A;
+  conv_pack_parity_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(dst), A, B, k, T, Cpad);
+  return check_launch("conv_pack_parity");
+}
+
+extern "C" int genrl_conv_pack_gather(void* stream, const float* w, void* dst, int A, int B, int k, int Cp) {
+  const long long total = (long long)A * k * k * Cp;
+  conv_pack_gather_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(dst), A, B, k, Cp);
+  return check_launch("conv_pack_gather");
+}
+
+extern "C" int genrl_conv_unpack_wgrad(void* stream, const float* dwp, long long ld, float* grad, int A, int B, int k, int Cp) {
+  const long long total = (long long)A * B * k * k;
+  conv_unpack_wgrad_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dwp, ld, grad, A, B,
+                                                                                                                                k * k, Cp);
+  return check_launch("conv_unpack_wgrad");
+}
+
+extern "C" int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, long long N, int C, int H, int W, int Cp) {
+  const long long total = N * H * W;
+  nchw_to_nhwc_pad_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, Cp);
+  return check_launch("nchw_to_nhwc_pad");
+}

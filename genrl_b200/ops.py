@@ -705,6 +705,61 @@ def lambda_return(reward, value, gamma, lam):
 # ---------------------------------------------------------------------------------------------------------------
 # conv stacks
 # ---------------------------------------------------------------------------------------------------------------
+
+# ---------------------------------------------------------------------------------------------------------------
+# implicit-GEMM convolutions (conv_igemm.cu): bf16 tensor-core mode, channel counts that are multiples of 8
+# ---------------------------------------------------------------------------------------------------------------
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+def conv_igemm_enabled(C):
+    import os
+    return _State.dtype == torch.bfloat16 and C % 8 == 0 and os.environ.get("GENRL_CONV_IGEMM", "1") != "0"
+
+
+def _rows_contig(t, C):
+    """NHWC rows [M, C] with ld == C (the gather addresses pixels as in[pix*C + c])"""
+    t = _check(t)
+    if t.dtype != torch.bfloat16 or _ld(t) != C or t.data_ptr() % 16:
+        out = torch.empty(t.shape[0], C, device=t.device, dtype=torch.bfloat16)
+        copy2d(t, out)
+        return out
+    return t
+
+
+def _igemm_gather(x, N, IH, IW, C, RH, RW, k, wm, ncols, bias, out=None):
+    """out[(n,yy,xx), col] = sum_{ky,kx,c} x[n, 2yy+ky, 2xx+kx, c] wm[col, (ky*k+kx)*C + c] (+bias): Conv2d fwd / ConvT dgrad"""
+    if out is None:
+        out = torch.empty(N * RH * RW, ncols, device=x.device, dtype=torch.bfloat16)
+    lib.genrl_conv_igemm_fwd(_st(), _p(x), N, IH, IW, C, RH, RW, 2, 1, k, k, _p(wm), _ld(wm), _pad16(ncols), ncols, 1, RH, RW, _p(out), 0, _p(bias))
+    return out
+
+
+def _igemm_subpixel(x, N, IH, IW, C, OH, OW, k, w_master, A, B, bias, nchw=False):
+    """out[n, oy, ox, b] = sum x[n, iy, ix, a] W4[a][b][oy-2iy][ox-2ix] (+bias): ConvTranspose2d fwd (W4 = its weight) / Conv2d dgrad"""
+    T = (k + 1) // 2
+    Cpad = _pad16(B)
+    wq = torch.empty(4 * Cpad, T * T * A, device=x.device, dtype=torch.bfloat16)
+    lib.genrl_conv_pack_parity(_st(), _p(w_master), _p(wq), A, B, k, Cpad)
+    if nchw:
+        out = torch.empty(N, B, OH, OW, device=x.device, dtype=torch.float32)
+    else:
+        out = torch.empty(N * OH * OW, B, device=x.device, dtype=torch.bfloat16)
+    lib.genrl_conv_igemm_fwd(_st(), _p(x), N, IH, IW, C, (OH + 1) // 2, (OW + 1) // 2, 1, -1, T, T, _p(wq), T * T * A, Cpad, B, 4, OH, OW, _p(out),
+                             int(nchw), _p(bias))
+    return out
+
+
+def _igemm_wgrad(src, N, IH, IW, C, RH, RW, k, S, Cs, w, A, B):
+    """grad(w)[a][b][ky][kx] += sum_rows S[row, a] src[n, 2yy+ky, 2xx+kx, b]   (src channel count C >= B, zero padded)"""
+    gbuf, ret = _grad_buf(w)
+    dwp = torch.zeros(Cs, k * k * C, device=src.device, dtype=torch.float32)
+    lib.genrl_conv_igemm_wgrad(_st(), _p(src), N, IH, IW, C, RH, RW, 2, k, k, _p(S), _ld(S), Cs, _p(dwp), k * k * C)
+    lib.genrl_conv_unpack_wgrad(_st(), _p(dwp), k * k * C, _p(gbuf), A, B, k, C)
+    return ret
+
+
 class _Conv2dS2(Function):
     """Conv2d(k, stride 2, no padding) on NHWC rows; x is uint8 NCHW for the first layer (preprocessing fused)."""
 
@@ -714,6 +769,13 @@ class _Conv2dS2(Function):
         Cout = w.shape[0]
         Kc = k * k * C
         dt = _State.dtype
+        ctx.igemm = (not u8) and conv_igemm_enabled(C) and Cout % 8 == 0
+        if ctx.igemm:
+            x = _rows_contig(x, C)
+            y = _igemm_gather(x, N, H, W, C, Ho, Wo, k, packed_conv_weight(w), Cout, b.detach())
+            ctx.save_for_backward(x)
+            ctx.w, ctx.b, ctx.geom = w, b, geom
+            return y
         col = empty_act(N * Ho * Wo, Kc, w.device, dt)
         lib.genrl_im2col(_st(), _p(x), -1 if u8 else _CODE[x.dtype], _p(col), _ld(col), _CODE[dt], N, H, W, C, k, Ho, Wo)
         wp = packed_conv_weight(w)
@@ -729,6 +791,16 @@ class _Conv2dS2(Function):
         w, b = ctx.w, ctx.b
         dy = as_compute(dy if dy.stride(-1) == 1 else dy.contiguous())
         dx = dw = db = None
+        if ctx.igemm:
+            x, Cout = col, w.shape[0]
+            dy = _rows_contig(dy, Cout)
+            if w.requires_grad:
+                dw = _igemm_wgrad(x, N, H, W, C, Ho, Wo, k, dy, Cout, w, Cout, C)
+                bbuf, db = _grad_buf(b)
+                lib.genrl_colsum(_st(), _p(dy), _ld(dy), _p(bbuf), dy.shape[0], dy.shape[1], _CODE[dy.dtype])
+            if ctx.needs_input_grad[0]:
+                dx = _igemm_subpixel(dy, N, Ho, Wo, Cout, H, W, k, w.detach(), Cout, C, None)
+            return dx, dw, db, None
         if w.requires_grad:
             gbuf, dw = _grad_buf(w)
             dwp = gemm(dy, col, trans_a=True, trans_w=True, out_dtype=torch.float32)            # [Cout, k*k*C]
@@ -758,6 +830,13 @@ class _ConvT2dS2(Function):
         Cin, Cout = w.shape[0], w.shape[1]
         x = as_compute(x)
         dt = _State.dtype
+        ctx.igemm = Hi > 1 and conv_igemm_enabled(Cin) and (nchw or Cout % 8 == 0)
+        if ctx.igemm:
+            x = _rows_contig(x, Cin)
+            y = _igemm_subpixel(x, N, Hi, Wi, Cin, Ho, Wo, k, w.detach(), Cin, Cout, b.detach(), nchw=nchw)
+            ctx.save_for_backward(x)
+            ctx.w, ctx.b, ctx.geom = w, b, geom
+            return y
         wt = packed_conv_weight(w)                                         # [Cin, k*k*Cout]
         col = gemm(x, wt, trans_w=True, out_dtype=dt)                      # [M, k*k*Cout]
         if nchw:
@@ -776,6 +855,26 @@ class _ConvT2dS2(Function):
         w, b = ctx.w, ctx.b
         Cin, Cout = w.shape[0], w.shape[1]
         dt = x.dtype
+        if ctx.igemm:
+            Cp = _pad8(Cout)
+            if nchw:
+                dyr = torch.empty(N * Ho * Wo, Cp, device=x.device, dtype=torch.bfloat16)
+                lib.genrl_nchw_to_nhwc_pad(_st(), _p(dy.contiguous().float()), _p(dyr), N, Cout, Ho, Wo, Cp)
+            else:
+                dyr = _rows_contig(dy if dy.stride(-1) == 1 else dy.contiguous(), Cout)
+            dx = dw = db = None
+            if w.requires_grad:
+                dw = _igemm_wgrad(dyr, N, Ho, Wo, Cp, Hi, Wi, k, x, Cin, w, Cin, Cout)
+                bbuf, db = _grad_buf(b)
+                lib.genrl_colsum(_st(), _p(dyr), Cp, _p(bbuf), dyr.shape[0], Cout, _CODE[dyr.dtype])
+            if ctx.needs_input_grad[0]:
+                if Cp == Cout:
+                    wg = packed_conv_weight(w)                                                     # [Cin, k*k*Cout]
+                else:
+                    wg = torch.empty(Cin, k * k * Cp, device=x.device, dtype=torch.bfloat16)
+                    lib.genrl_conv_pack_gather(_st(), _p(w.detach()), _p(wg), Cin, Cout, k, Cp)
+                dx = _igemm_gather(dyr, N, Ho, Wo, Cp, Hi, Wi, k, wg, Cin, None)
+            return dx, dw, db, None
         if nchw:
             dyr = torch.empty(N * Ho * Wo, Cout, device=x.device, dtype=dt)
             lib.genrl_nchw_to_nhwc(_st(), _p(dy.contiguous().float()), _p(dyr), _CODE[dt], N, Cout, Ho, Wo)

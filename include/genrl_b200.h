@@ -102,6 +102,24 @@ int genrl_im2col(void* stream, const void* x, int x_dtype, void* col, long long 
 int genrl_col2im(void* stream, const void* col, long long ldcol, int col_dtype, const float* bias, void* y, int y_dtype, int nchw_out, int N,
                  int Hi, int Wi, int C, int k, int Ho, int Wo);
 int genrl_nchw_to_nhwc(void* stream, const float* x, void* y, int y_dtype, int N, int C, int H, int W);
+
+/* Implicit-GEMM convolutions on tcgen05 (no im2col / col2im buffers), NHWC bf16 activations; replace the lowered
+ * nn.Conv2d(k4,s2) / nn.ConvTranspose2d(k5|k6,s2) passes of Encoder/Decoder (dreamer_utils.py:580-589, :656-671).
+ * Virtual im2col element: col[(n,yy,xx), ((a*tw+b)*C+c)] = in[n, yy*sy + a*ts, xx*sy + b*ts, c] (zero outside the image).
+ *   genrl_conv_igemm_fwd  : out[row, col] = sum_k col[row,k] Wm[col,k] + bias; ncls==1: gather form (Conv2d fwd, ConvT dgrad);
+ *                           ncls==4: sub-pixel form, column block cls=(py,px) goes to pixel (2yy+py, 2xx+px) (ConvT fwd, Conv2d dgrad).
+ *                           out_mode 0: NHWC bf16 rows [Nimg*OH*OW, Cout]; 1: NCHW fp32.
+ *   genrl_conv_igemm_wgrad: dw[s, k] += sum_rows S[row, s] col[row, k]  (fp32 atomics, split over the rows).
+ *   genrl_conv_pack_parity / _pack_gather / _unpack_wgrad: filter layouts of the two forms from/to the [A,B,k,k] fp32 master. */
+int genrl_conv_igemm_fwd(void* stream, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int ts, int th, int tw,
+                         const void* Wm, long long ldw, int Cpad, int Cout, int ncls, int OH, int OW, void* out, int out_mode,
+                         const float* bias);
+int genrl_conv_igemm_wgrad(void* stream, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int th, int tw,
+                           const void* S, long long lds, int Cs, float* dw, long long lddw);
+int genrl_conv_pack_parity(void* stream, const float* w, void* dst, int A, int B, int k, int Cpad);
+int genrl_conv_pack_gather(void* stream, const float* w, void* dst, int A, int B, int k, int Cp);
+int genrl_conv_unpack_wgrad(void* stream, const float* dwp, long long ld, float* grad, int A, int B, int k, int Cp);
+int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, long long N, int C, int H, int W, int Cp);
 int genrl_permute_abp(void* stream, const void* src, int src_dtype, void* dst, int dst_dtype, long long A, int B, int P, int accumulate);
 
 /* Fused direct kernels for the 3-channel ends of the conv stacks (Encoder layer 0 + ImgChLayerNorm + SiLU, dreamer_utils.py:580-589;

@@ -250,7 +250,8 @@ def test_lambda_return():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("N,H,Cin,Cout,k", [(3, 64, 3, 8, 4), (2, 31, 8, 16, 4), (2, 14, 16, 24, 4), (5, 6, 24, 32, 4)])
+@pytest.mark.parametrize("N,H,Cin,Cout,k", [(3, 64, 3, 8, 4), (2, 31, 8, 16, 4), (2, 14, 16, 24, 4), (5, 6, 24, 32, 4), (3, 31, 48, 96, 4), (2, 14, 96, 192, 4),
+                                             (7, 6, 192, 384, 4)])
 def test_conv2d_s2(dtype, N, H, Cin, Cout, k):
     with ops.use_dtype(dtype):
         conv = torch.nn.Conv2d(Cin, Cout, k, stride=2)
@@ -283,7 +284,8 @@ def test_conv2d_s2(dtype, N, H, Cin, Cout, k):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("N,Hi,Cin,Cout,k,last", [(3, 1, 32, 16, 5, False), (2, 5, 16, 8, 5, False), (2, 13, 8, 8, 6, False), (2, 30, 8, 3, 6, True)])
+@pytest.mark.parametrize("N,Hi,Cin,Cout,k,last", [(3, 1, 32, 16, 5, False), (2, 5, 16, 8, 5, False), (2, 13, 8, 8, 6, False), (2, 30, 8, 3, 6, True),
+                                                   (5, 5, 192, 96, 5, False), (3, 13, 96, 48, 6, False), (2, 30, 48, 3, 6, True)])
 def test_conv_transpose2d_s2(dtype, N, Hi, Cin, Cout, k, last):
     with ops.use_dtype(dtype):
         conv = torch.nn.ConvTranspose2d(Cin, Cout, k, stride=2)
