@@ -64,8 +64,12 @@ __device__ __forceinline__ float silu_gradf_(float x) {
 }
 
 // bf16 mode uses the SFU fast paths (ex2/rcp approximations, ~2 ulp): activations are rounded to bf16 right after anyway.
+// (MUFU.EX2 + MUFU.RCP / MUFU.TANH as single instructions: the IEEE __frcp_rn / non-ftz __expf forms cost a slow-path branch per element,
+// which made the row kernels instruction-issue bound)
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <bool FAST> __device__ __forceinline__ float sigm_t(float x) {
-  if (FAST) return __frcp_rn(1.0f + __expf(-x));
+  if (FAST) return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * x));
   return 1.0f / (1.0f + expf(-x));
 }
 template <bool FAST> __device__ __forceinline__ float silu_t(float x) { return x * sigm_t<FAST>(x); }
@@ -74,7 +78,7 @@ template <bool FAST> __device__ __forceinline__ float silu_grad_t(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 template <bool FAST> __device__ __forceinline__ float tanh_t(float x) {
-  if (FAST) return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
+  if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
   return tanhf(x);
 }
 

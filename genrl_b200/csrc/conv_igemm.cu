@@ -21,13 +21,23 @@ constexpr int CV_THREADS = 192;
 constexpr int CV_GATHER = 128;     // gather threads (warps 2..5)
 constexpr int CV_LAG = 2;          // cp.async groups kept in flight per gather thread before the stage is published
 
+// .ca: every input pixel is gathered by several taps of the same CTA (4 for k4/s2, 9 for the 3x3 sub-pixel taps); the CTA's input
+// footprint (~20 KB) stays in L1, so the re-reads do not go back to L2
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// exact x / d for x < 2^24, d < 2^12 as one 64-bit multiply: q = (x * M) >> 40, M = floor(2^40 / d) + 1   (M = 0: plain division)
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t d, unsigned long long M) {
+  return M ? (uint32_t)(((unsigned long long)x * M) >> 40) : x / d;
+}
+static unsigned long long div_magic(long long xmax, int d) {
+  return (xmax < (1LL << 24) && d > 0 && d < (1 << 12)) ? ((1ULL << 40) / (unsigned long long)d + 1ULL) : 0ULL;
 }
 
 struct ConvGeom {
@@ -37,7 +47,24 @@ struct ConvGeom {
   int sy, ts, tw;            // input stride of the row grid, tap direction (+1/-1), taps along x
   int K;                     // th*tw*C
   long long rows;            // Nimg*RH*RW
+  unsigned long long m_rhw, m_rw, m_c, m_tw;   // fast_div magics for RH*RW, RW, C, tw
 };
+
+// row -> (n, yy, xx) of the row grid
+__device__ __forceinline__ void decode_row(const ConvGeom& g, long long row, int rhw, long long& n, int& yy, int& xx) {
+  const uint32_t r = (uint32_t)row;
+  const uint32_t nn = g.m_rhw ? fast_div(r, (uint32_t)rhw, g.m_rhw) : (uint32_t)(row / rhw);
+  const uint32_t rem = (uint32_t)(row - (long long)nn * rhw);
+  const uint32_t y = fast_div(rem, (uint32_t)g.RW, g.m_rw);
+  n = nn; yy = (int)y; xx = (int)(rem - y * g.RW);
+}
+// kidx -> (tap row a, tap col b, channel c)
+__device__ __forceinline__ void decode_k(const ConvGeom& g, int kidx, int& a, int& b, int& c) {
+  const uint32_t tap = fast_div((uint32_t)kidx, (uint32_t)g.C, g.m_c);
+  c = kidx - (int)tap * g.C;
+  a = (int)fast_div(tap, (uint32_t)g.tw, g.m_tw);
+  b = (int)tap - a * g.tw;
+}
 
 struct ConvFwdParams {
   ConvGeom g;
@@ -146,9 +173,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
     for (int i = 0; i < 8; ++i) {
       const long long row = m0 + rg + 16 * i;
       if (row < g.rows) {
-        const long long n = row / rhw;
-        const int rem = (int)(row - n * rhw);
-        const int yy = rem / g.RW, xx = rem - yy * g.RW;
+        long long n; int yy, xx;
+        decode_row(g, row, rhw, n, yy, xx);
         img[i] = g.in + n * ((long long)g.IH * g.IW * g.C);
         yx0[i] = ((yy * g.sy + 4096) << 16) | (xx * g.sy + 4096);       // biased so negative tap offsets stay positive
       } else {
@@ -163,10 +189,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
       mbar_wait(&empty_bar[stage], phase ^ 1);
       const int kidx = kb * CV_BK + j * 8;
       const bool kval = kidx < g.K;
-      const int tap = kidx / g.C;
-      const int c = kidx - tap * g.C;
-      const int a = tap / g.tw;
-      const int b = tap - a * g.tw;
+      int a, b, c;
+      decode_k(g, kidx, a, b, c);
       const int dy = a * g.ts, dx = b * g.ts;
       const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) + dst_off;
 #pragma unroll
@@ -194,7 +218,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
     const long long row = m0 + quarter * 32 + lane;
     const bool row_ok = row < g.rows;
     long long n = 0; int yy = 0, xx = 0;
-    if (row_ok) { n = row / rhw; const int rem = (int)(row - n * rhw); yy = rem / g.RW; xx = rem - yy * g.RW; }
+    if (row_ok) decode_row(g, row, rhw, n, yy, xx);
 #pragma unroll 1
     for (int cc = 0; cc < BN; cc += 32) {
       if (n0 + cc >= p.N) break;
@@ -338,10 +362,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
     for (int q = 0; q < NG; ++q) {
       const int kidx = n0 + q * 64 + j * 8;
       kval[q] = kidx < g.K;
-      const int tap = kidx / g.C;
-      const int c = kidx - tap * g.C;
-      const int a = tap / g.tw;
-      const int b = tap - a * g.tw;
+      int a, b, c;
+      decode_k(g, kidx, a, b, c);
       kdy[q] = a * g.ts; kdx[q] = b * g.ts;
       koff[q] = ((long long)kdy[q] * g.IW + kdx[q]) * g.C + c;
     }
@@ -356,9 +378,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
       for (int i = 0; i < 4; ++i) {
         const long long row = (long long)(kb_begin + kb) * CV_BK + rg + 16 * i;
         const bool rok = row < g.rows;
-        const long long n = rok ? row / rhw : 0;
-        const int rem = rok ? (int)(row - n * rhw) : 0;
-        const int yy = rem / g.RW, xx = rem - yy * g.RW;
+        long long n = 0; int yy = 0, xx = 0;
+        if (rok) decode_row(g, row, rhw, n, yy, xx);
         const int iy0 = yy * g.sy, ix0 = xx * g.sy;
         const __nv_bfloat16* base = g.in + ((n * g.IH + iy0) * g.IW + ix0) * g.C;
 #pragma unroll
@@ -488,6 +509,10 @@ static int fill_geom(ConvGeom* g, const void* in, int Nimg, int IH, int IW, int 
   g->Nimg = Nimg; g->IH = IH; g->IW = IW; g->C = C; g->RH = RH; g->RW = RW; g->sy = sy; g->ts = ts; g->tw = tw;
   g->K = th * tw * C;
   g->rows = (long long)Nimg * RH * RW;
+  g->m_rhw = div_magic(g->rows, RH * RW);
+  g->m_rw = div_magic(RH * RW, RW);
+  g->m_c = div_magic(g->K + 64 + 256, C);
+  g->m_tw = div_magic(th * tw + 64, tw);
   return 0;
 }
 

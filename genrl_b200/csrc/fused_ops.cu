@@ -941,8 +941,12 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
   DISPATCH_T(dtype, {
     if (!dgamma && D % 8 == 0 && vec_ok<T>(z, ldz) && vec_ok<T>(dz, lddz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(dh, lddh) &&
         (!dhprev || vec_ok<float>(dhprev, lddhp)) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-      gru_bwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
-                                                                           dhprev, lddhp, M, D);
+      if (D == 1024)
+        gru_bwd_row1024_kernel<T><<<(int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
+                                                                                               (T*)dz, lddz, dhprev, lddhp, M);
+      else
+        gru_bwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+                                                                             dhprev, lddhp, M, D);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(gru_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       gru_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,

@@ -483,6 +483,49 @@ __global__ void __launch_bounds__(256) gru_bwd_fast_kernel(const float* __restri
   }
 }
 
+// frozen-weights GRU backward, one 128-thread block per row of D = 1024: each thread owns 8 hidden units, gates and partial
+// gradients stay in registers (z, h, dh are read once), the two LayerNorm row sums go through a 4-warp shared-memory reduction
+template <typename T>
+__global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __restrict__ dh, long long lddh, const T* __restrict__ z, long long ldz,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
+                                                              T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M) {
+  constexpr int D = 1024, D3 = 3072;
+  __shared__ float red[2][4];
+  const int j = threadIdx.x * 8, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float gr[8], gc[8], gu[8];
+  ldf8(gamma + j, gr); ldf8(gamma + D + j, gc); ldf8(gamma + 2 * D + j, gu);
+  for (long long row = blockIdx.x; row < M; row += gridDim.x) {
+    const T* zr_ = z + row * ldz;
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float a[8], b[8], c[8], r[8], cand[8], u[8], pc[8], xr[8], xc[8], xu[8], h[8], g[8];
+    V8<T>::load(zr_ + j, a); V8<T>::load(zr_ + D + j, b); V8<T>::load(zr_ + 2 * D + j, c);
+    ldf8(hprev + row * ldh + j, h); ldf8(dh + row * lddh + j, g);
+    gru_gate8<(sizeof(T) == 2)>(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float drc = g[k] * u[k] * (1.0f - cand[k] * cand[k]);
+      a[k] = drc * pc[k] * r[k] * (1.0f - r[k]) * gr[k];              // reuse a,b,c as the three gate gradients
+      b[k] = drc * r[k] * gc[k];
+      c[k] = g[k] * (cand[k] - h[k]) * u[k] * (1.0f - u[k]) * gu[k];
+      s1 += a[k] + b[k] + c[k]; s2 += a[k] * xr[k] + b[k] * xc[k] + c[k] * xu[k];
+      h[k] = g[k] * (1.0f - u[k]);                                     // dhprev
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    __syncthreads();                                                   // red[] of the previous row is no longer read
+    if (lane == 0) { red[0][w] = s1; red[1][w] = s2; }
+    __syncthreads();
+    const float m1 = (red[0][0] + red[0][1] + red[0][2] + red[0][3]) / D3, m2 = (red[1][0] + red[1][1] + red[1][2] + red[1][3]) / D3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a[k] = rstd * (a[k] - m1 - xr[k] * m2); b[k] = rstd * (b[k] - m1 - xc[k] * m2); c[k] = rstd * (c[k] - m1 - xu[k] * m2);
+    }
+    V8<T>::store(dz + row * lddz + j, a); V8<T>::store(dz + row * lddz + D + j, b); V8<T>::store(dz + row * lddz + 2 * D + j, c);
+    if (dhprev) V8<float>::store(dhprev + row * lddhp + j, h);
+  }
+}
+
 // ---- vectorised strided copy / row gather with cast -------------------------------------------------------------------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const TI* __restrict__ src, long long lds, const int* __restrict__ idx,

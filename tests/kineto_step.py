@@ -25,6 +25,14 @@ def _logged(*a):
     shapes.append((a[1], a[2], a[3], a[6], a[9], a[13], a[15]))     # M N K transA transW c_dtype accumulate
     return _orig(*a)
 lib.__dict__["genrl_gemm"] = _logged
+ln_calls = {"genrl_ln_act_fwd": [], "genrl_ln_act_bwd": []}
+def _wrap(name, mi):
+    orig = getattr(lib, name)
+    def f(*a):
+        ln_calls[name].append((a[mi], a[mi + 1], bool(a[11]) if name.endswith("bwd") else None))
+        return orig(*a)
+    lib.__dict__[name] = f
+_wrap("genrl_ln_act_fwd", 10); _wrap("genrl_ln_act_bwd", 14)
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(3)
     torch.cuda.synchronize()
@@ -48,3 +56,22 @@ if len(gem) == len(shapes):
     print("GEMM by shape (warm, kineto):   ms  calls  us/call  TFLOP/s  (M N K tA tW cdt acc)")
     for sh, (us, n) in sorted(ag.items(), key=lambda kv: -kv[1][0])[:40]:
         print(f"{us/1e3:7.3f} {n:5d} {us/n:9.1f} {2.0*sh[0]*sh[1]*sh[2]*n/us/1e6:9.1f}   {sh}")
+
+# implicit-GEMM conv launches in issue order (fwd: enc L1..L3 gather, dec D1..D3 sub-pixel; bwd: D3..D1 gather dgrad, L3..L1 sub-pixel dgrad)
+for pat in ("conv_fwd_kernel", "conv_wgrad_kernel", "im2col", "col2im"):
+    evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and pat in e.name], key=lambda e: e.time_range.start)
+    print(pat, " ".join(f"{(e.device_time_total if hasattr(e, 'device_time_total') else e.cuda_time_total):.0f}" for e in evs), "us")
+
+# LayerNorm launches by shape
+def _t(e): return e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+for cname, pats in (("genrl_ln_act_fwd", ("ln_fwd_fast_kernel", "ln_act_fwd_kernel")), ("genrl_ln_act_bwd", ("ln_bwd_colg_kernel", "ln_bwd_fast_kernel", "ln_act_bwd_kernel"))):
+    evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and any(p in e.name for p in pats)], key=lambda e: e.time_range.start)
+    calls = ln_calls[cname]
+    print(cname, len(evs), len(calls))
+    if len(evs) == len(calls):
+        ag = collections.OrderedDict()
+        for e, c in zip(evs, calls):
+            d = ag.setdefault(c, [0.0, 0]); d[0] += _t(e); d[1] += 1
+        for c, (us, n) in sorted(ag.items(), key=lambda kv: -kv[1][0])[:14]:
+            M, D = c[0], c[1]
+            print(f"  {us/1e3:7.3f} ms {n:4d} calls {us/n:8.1f} us/call  {M*D*2*(2 if c[2] is None else 3)/(us/n)/1e3:7.0f} GB/s  {c}")

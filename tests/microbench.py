@@ -40,6 +40,7 @@ with ops.use_dtype(bf):
         P = lambda t: t.data_ptr()
         timeit(f"ln_act_fwd {M}x{D}", lambda: lib.genrl_ln_act_fwd(ops._st(), P(x), D, P(g), P(b), 1e-5, 1, P(y), D, P(st), M, D, 1), bytes_=M * D * 4)
         timeit(f"ln_act_bwd (frozen) {M}x{D}", lambda: lib.genrl_ln_act_bwd(ops._st(), P(dy), D, P(x), D, P(g), P(b), P(st), 1, P(dx), D, None, None, None, M, D, 1), bytes_=M * D * 6)
+        timeit(f"ln_colgrad alone {M}x{D}", lambda: lib.genrl_ln_colgrad(ops._st(), P(dy), D, P(x), D, P(dx), D, P(g), P(b), P(st), 1, P(dg), P(db), P(dl), M, D, 1), bytes_=M * D * 6)
         timeit(f"ln_act_bwd (+colgrad) {M}x{D}", lambda: lib.genrl_ln_act_bwd(ops._st(), P(dy), D, P(x), D, P(g), P(b), P(st), 1, P(dx), D, P(dg), P(db), P(dl), M, D, 1), bytes_=M * D * 12)
     M = 2400
     a, b2 = R(M, 1024), R(M, 1024)

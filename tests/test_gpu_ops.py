@@ -143,6 +143,31 @@ def test_gru_gates(dtype):
         close(bd.grad, br.grad, msg="gru dbeta", **tol)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gru_gates_frozen_d1024(dtype):
+    """imagination path: frozen GRU LayerNorm parameters, D = 1024 (block-per-row backward kernel)"""
+    M, D = 301, 1024
+    with ops.use_dtype(dtype):
+        z = rnd(M, 3 * D).to(dtype)
+        h = rnd(M, D, seed=1)
+        g, b = 1 + 0.1 * rnd(3 * D, seed=2), 0.1 * rnd(3 * D, seed=3)
+        dh = rnd(M, D, seed=4)
+        zr = z.float().clone().requires_grad_(True); hr = h.clone().requires_grad_(True)
+        parts = F.layer_norm(zr, (3 * D,), g, b, 1e-5)
+        r, c, u = torch.chunk(parts, 3, -1)
+        r = torch.sigmoid(r); c = torch.tanh(r * c); u = torch.sigmoid(u - 1)
+        out = u * c + (1 - u) * hr
+        out.backward(dh)
+        zd = z.to(DEV).requires_grad_(True); hd = h.to(DEV).requires_grad_(True)
+        gd = torch.nn.Parameter(g.to(DEV), requires_grad=False); bd = torch.nn.Parameter(b.to(DEV), requires_grad=False)
+        od = ops.gru_gates(zd, gd, bd, hd)
+        od.backward(dh.to(DEV))
+        tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+        close(od, out, msg="gru h", **tol)
+        close(zd.grad, zr.grad, msg="gru dz", **tol)
+        close(hd.grad, hr.grad, msg="gru dh", **tol)
+
+
 @pytest.mark.parametrize("S,K", [(8, 8), (32, 32), (4, 48)])
 def test_cat_sample(S, K):
     rows = 50
