@@ -7,18 +7,21 @@
 //   sub-pixel form (sy = 1, ts = -1, taps T x T,     : ConvTranspose2d forward, Conv2d dgrad           -> conv_fwd_kernel
 //      T = ceil(k/2), 4 output parity classes stacked along N: out[n, 2yy+py, 2xx+px, co])
 //   weight gradients (gather form, K = pixels)       : dW[s, kidx] = sum_rows S[row, s] * col[row, kidx] -> conv_wgrad_kernel
-// Warp roles: warp 0 = TMA (filters / S matrix), warp 1 = TMEM allocator + MMA issuer, warps 2..5 = cp.async gather producers
-// during the main loop, then the epilogue (tcgen05.ld -> bias -> NHWC bf16 or NCHW fp32 stores / fp32 atomics for split-K wgrad).
+// Warp roles: warp 0 = TMA (filters / S matrix), warp 1 = TMEM allocator + MMA issuer, warps 2..5 = cp.async gather producers;
+// epilogue (tcgen05.ld -> bias -> NHWC bf16 or NCHW fp32 stores / fp32 atomics for split-K wgrad) on warps 6..9 of the persistent forward
+// kernel (overlapped with the next tile through a second TMEM accumulator) and on the gather warps of the wgrad kernel.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace genrl {
 
 constexpr int CV_BM = 128;
 constexpr int CV_BK = 64;
 constexpr int CV_THREADS = 192;
-constexpr int CV_GATHER = 128;     // gather threads (warps 2..5)
+constexpr int CV_GATHER = 128;     // gather threads of the wgrad kernel (warps 2..5)
+constexpr int CVF_GATHER = 256;    // gather threads of the forward kernel (warps 2..9)
 constexpr int CV_LAG = 2;          // cp.async groups kept in flight per gather thread before the stage is published
 
 // .ca: every input pixel is gathered by several taps of the same CTA (4 for k4/s2, 9 for the 3x3 sub-pixel taps); the CTA's input
@@ -44,7 +47,7 @@ struct ConvGeom {
   const __nv_bfloat16* in;   // [Nimg, IH, IW, C] NHWC
   int Nimg, IH, IW, C;
   int RH, RW;                // row grid per image
-  int sy, ts, tw;            // input stride of the row grid, tap direction (+1/-1), taps along x
+  int sy, ts, th, tw;        // input stride of the row grid, tap direction (+1/-1), taps along y / x
   int K;                     // th*tw*C
   long long rows;            // Nimg*RH*RW
   unsigned long long m_rhw, m_rw, m_c, m_tw;   // fast_div magics for RH*RW, RW, C, tw
@@ -57,6 +60,23 @@ __device__ __forceinline__ void decode_row(const ConvGeom& g, long long row, int
   const uint32_t rem = (uint32_t)(row - (long long)nn * rhw);
   const uint32_t y = fast_div(rem, (uint32_t)g.RW, g.m_rw);
   n = nn; yy = (int)y; xx = (int)(rem - y * g.RW);
+}
+// per-row gather state: 32-bit element offset of the row's base pixel and the bitmask of taps that fall inside the image
+// (bits 0..7: tap rows a, bits 8..15: tap columns b); off < 0 marks a row past the end of the row grid
+__device__ __forceinline__ void row_state(const ConvGeom& g, long long row, int rhw, int& off, int& mask) {
+  off = -1; mask = 0;
+  if (row < g.rows) {
+    long long n; int yy, xx;
+    decode_row(g, row, rhw, n, yy, xx);
+    const int iy0 = yy * g.sy, ix0 = xx * g.sy;
+    off = (int)(((n * g.IH + iy0) * g.IW + ix0) * g.C);
+    // taps a with 0 <= iy0 + a*ts < IH form a contiguous range [lo, hi]
+    const int ylo = g.ts > 0 ? 0 : max(0, iy0 - g.IH + 1), yhi = g.ts > 0 ? min(g.th, g.IH - iy0) - 1 : min(g.th - 1, iy0);
+    const int xlo = g.ts > 0 ? 0 : max(0, ix0 - g.IW + 1), xhi = g.ts > 0 ? min(g.tw, g.IW - ix0) - 1 : min(g.tw - 1, ix0);
+    const int my = yhi >= ylo ? (int)(((2u << yhi) - 1u) & ~((1u << ylo) - 1u)) : 0;
+    const int mx = xhi >= xlo ? (int)(((2u << xhi) - 1u) & ~((1u << xlo) - 1u)) : 0;
+    mask = my | (mx << 8);
+  }
 }
 // kidx -> (tap row a, tap col b, channel c)
 __device__ __forceinline__ void decode_k(const ConvGeom& g, int kidx, int& a, int& b, int& c) {
@@ -90,36 +110,66 @@ __device__ __forceinline__ void publish_stage(uint64_t* bar) {
   mbar_arrive(bar);
 }
 
+// after the last issued k-block: publish the D = LAG .. 1 most recent stages in order
+template <int D, int STAGES> struct DrainStages {
+  static __device__ __forceinline__ void run(long long gs, uint64_t* full_bar) {
+    if (gs >= D) { cp_async_wait<D - 1>(); publish_stage(&full_bar[(int)((gs - D) % STAGES)]); }
+    DrainStages<D - 1, STAGES>::run(gs, full_bar);
+  }
+};
+template <int STAGES> struct DrainStages<0, STAGES> {
+  static __device__ __forceinline__ void run(long long, uint64_t*) {}
+};
+
+// shared-memory stages of the forward kernel.  The L1 that is left over matters: every input pixel is re-read by 4..9 taps, and
+// the 5/6-stage variants measured 20-30 % slower on the wide tiles than 4 stages (profiles/r01_conv_notes.md)
+template <int BN> struct FwdCfg {
+  static constexpr int STAGES = BN <= 96 ? 3 : 4;      // measured: deeper rings do not help (the gather is not latency bound) and cost L1 capacity
+  static constexpr int LAG = STAGES - 1;
+  static constexpr int CTAS = BN <= 96 ? 2 : 1;
+};
+
 // =================================================================================================
 // forward-type kernel: D[row, col] = sum_k col[row, k] * Wm[col, k]
+// Persistent: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; two TMEM accumulators so the epilogue warps (10..13) drain tile i
+// while the gather warps (2..9), the TMA lane and the MMA lane already work on tile i+1 (most of these layers have only 4..27 k-blocks
+// per tile, so an un-overlapped epilogue + CTA prologue would cost as much as the main loop).
 // =================================================================================================
+constexpr int CVF_THREADS = 448;     // TMA warp, MMA warp, 8 gather warps, 4 epilogue warps
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(CV_THREADS, (BN <= 96 ? 2 : 1))
+__global__ void __launch_bounds__(CVF_THREADS, (BN <= 96 ? 2 : 1))
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int LAG = STAGES - 1;
   constexpr int A_BYTES = CV_BM * CV_BK * 2;
   constexpr int B_BYTES = BN * CV_BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;      // TMEM columns of one accumulator
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long m0 = (long long)blockIdx.x * CV_BM;
-  const int n0 = blockIdx.y * BN;
   const int nkb = p.num_kb;
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const long long tiles = ((p.g.rows + CV_BM - 1) / CV_BM) * tiles_n;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CV_GATHER + 1);
+      mbar_init(&full_bar[s], CVF_GATHER + 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -132,135 +182,143 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ------------------------------ TMA: filter k-blocks ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], B_BYTES);
-        tma_load_2d(&tmW, &full_bar[stage], smem + stage * STAGE_BYTES + A_BYTES, kb * CV_BK, n0);     // box {64 k, BN n}
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (int)(t % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 64);
+          mbar_expect_tx(&full_bar[stage], B_BYTES);
+          tma_load_2d(&tmW, &full_bar[stage], smem + stage * STAGE_BYTES + A_BYTES, kb * CV_BK, n0);     // box {64 k, BN n}
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CV_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_sleep(&tempty_bar[buf], ((it >> 1) & 1) ^ 1, 32);              // epilogue has drained this accumulator (first use passes)
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * ACC_COLS);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_sleep(&full_bar[stage], phase, 20);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < CV_BK / 16; ++k)
-          umma_bf16(tmem_base, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
-        if (kb == nkb - 1) umma_commit(tmem_full_bar);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < CV_BK / 16; ++k)
+            umma_bf16(acc, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull_bar[buf]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
-  } else {
-    // ------------------------------ gather producers ------------------------------
+  } else if (warp < 10) {
+    // ------------------------------ gather producers (warps 2..9): thread = (16-byte chunk j, rows rg + 32 i) ------------------------------
     const ConvGeom& g = p.g;
-    const int t = threadIdx.x - 64;
-    const int j = t & 7;                     // 16-byte chunk of the 64-wide k block
-    const int rg = t >> 3;                   // rows rg + 16*i
-    const __nv_bfloat16* img[8];
-    int yx0[8];
+    const int t256 = threadIdx.x - 64;
+    const int j = t256 & 7;                  // 16-byte chunk of the 64-wide k block
+    const int rg = t256 >> 3;                // rows rg + 32*i, i < 4
     const int rhw = g.RH * g.RW;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long row = m0 + rg + 16 * i;
-      if (row < g.rows) {
-        long long n; int yy, xx;
-        decode_row(g, row, rhw, n, yy, xx);
-        img[i] = g.in + n * ((long long)g.IH * g.IW * g.C);
-        yx0[i] = ((yy * g.sy + 4096) << 16) | (xx * g.sy + 4096);       // biased so negative tap offsets stay positive
-      } else {
-        img[i] = nullptr;
-        yx0[i] = 0;
-      }
-    }
     const uint32_t dst_off = (uint32_t)(rg * 128 + ((j ^ (rg & 7)) << 4));
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      const int kidx = kb * CV_BK + j * 8;
-      const bool kval = kidx < g.K;
-      int a, b, c;
-      decode_k(g, kidx, a, b, c);
-      const int dy = a * g.ts, dx = b * g.ts;
-      const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) + dst_off;
+    long long gs = 0;                        // k-blocks issued so far (across tiles): publishing lags LAG behind issuing
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const long long m0 = (t / tiles_n) * CV_BM;
+      int off[4], mask[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int iy = (yx0[i] >> 16) - 4096 + dy, ix = (yx0[i] & 0xffff) - 4096 + dx;
-        const bool ok = kval && img[i] != nullptr && (unsigned)iy < (unsigned)g.IH && (unsigned)ix < (unsigned)g.IW;
-        const void* src = ok ? (const void*)(img[i] + ((long long)iy * g.IW + ix) * g.C + c) : (const void*)g.in;
-        cp_async16(sa + i * (16 * 128), src, ok ? 16u : 0u);
+      for (int i = 0; i < 4; ++i) row_state(g, m0 + rg + 32 * i, rhw, off[i], mask[i]);
+      for (int kb = 0; kb < nkb; ++kb, ++gs) {
+        mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
+        const int kidx = kb * CV_BK + j * 8;
+        int a, b, c;
+        decode_k(g, kidx, a, b, c);
+        const int koff = (a * g.IW + b) * g.ts * g.C + c;
+        const int kbit = kidx < g.K ? ((1 << a) | (256 << b)) : 0x10000;       // bit 16 is never set in a row mask
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) + dst_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = (mask[i] & kbit) == kbit;
+          cp_async16(sa + i * (32 * 128), g.in + (ok ? off[i] + koff : 0), ok ? 16u : 0u);
+        }
+        cp_async_commit();
+        if (gs >= LAG) {
+          cp_async_wait<LAG>();
+          publish_stage(&full_bar[(int)((gs - LAG) % STAGES)]);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      cp_async_commit();
-      if (kb >= CV_LAG) {
-        cp_async_wait<CV_LAG>();
-        publish_stage(&full_bar[(kb - CV_LAG) % STAGES]);
-      }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    if (nkb >= 2) { cp_async_wait<1>(); publish_stage(&full_bar[(nkb - 2) % STAGES]); }
-    cp_async_wait<0>();
-    publish_stage(&full_bar[(nkb - 1) % STAGES]);
-
-    // ------------------------------ epilogue ------------------------------
-    const int quarter = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const long long row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < g.rows;
-    long long n = 0; int yy = 0, xx = 0;
-    if (row_ok) decode_row(g, row, rhw, n, yy, xx);
+    DrainStages<LAG, STAGES>::run(gs, full_bar);
+  } else {
+    // ------------------------------ epilogue (warps 10..13) ------------------------------
+    const ConvGeom& g = p.g;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int rhw = g.RH * g.RW;
+    int it = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const long long m0 = (t / tiles_n) * CV_BM;
+      const int n0 = (int)(t % tiles_n) * BN;
+      mbar_wait_sleep(&tfull_bar[buf], (it >> 1) & 1, 128);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * ACC_COLS) + ((uint32_t)(quarter * 32) << 16);
+      const long long row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < g.rows;
+      long long n = 0; int yy = 0, xx = 0;
+      if (row_ok) decode_row(g, row, rhw, n, yy, xx);
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 32) {
-      if (n0 + cc >= p.N) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cc, v);
-      if (!row_ok) continue;
+      for (int cc = 0; cc < BN; cc += 32) {
+        if (n0 + cc >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(acc + (uint32_t)cc, v);
+        if (!row_ok) continue;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int col = n0 + cc + 16 * h;
-        if (col >= p.N || cc + 16 * h >= BN) continue;
-        const int cls = col / p.Cpad;
-        const int co0 = col - cls * p.Cpad;
-        const int nco = min(16, p.Cout - co0);
-        if (nco <= 0) continue;
-        int oy = yy, ox = xx;
-        if (p.ncls > 1) { oy = 2 * yy + (cls >> 1); ox = 2 * xx + (cls & 1); }
-        if (oy >= p.OH || ox >= p.OW) continue;
-        float f[16];
+        for (int h = 0; h < 4; ++h) {
+          const int col = n0 + cc + 8 * h;
+          if (col >= p.N || cc + 8 * h >= BN) continue;
+          const int cls = col / p.Cpad;
+          const int co0 = col - cls * p.Cpad;
+          const int nco = min(8, p.Cout - co0);
+          if (nco <= 0) continue;
+          int oy = yy, ox = xx;
+          if (p.ncls > 1) { oy = 2 * yy + (cls >> 1); ox = 2 * xx + (cls & 1); }
+          if (oy >= p.OH || ox >= p.OW) continue;
+          float f[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) f[q] = __uint_as_float(v[16 * h + q]) + ((p.bias != nullptr && q < nco) ? __ldg(p.bias + co0 + q) : 0.f);
-        if (p.out_mode == 0) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((n * p.OH + oy) * p.OW + ox) * p.Cout + co0;
-          if (nco == 16 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-            for (int q = 0; q < 16; q += 8) {
+          for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * h + q]) + ((p.bias != nullptr && q < nco) ? __ldg(p.bias + co0 + q) : 0.f);
+          if (p.out_mode == 0) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((n * p.OH + oy) * p.OW + ox) * p.Cout + co0;
+            if (nco == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
               uint4 pk;
-              __nv_bfloat162 a0 = __floats2bfloat162_rn(f[q], f[q + 1]), a1 = __floats2bfloat162_rn(f[q + 2], f[q + 3]);
-              __nv_bfloat162 a2 = __floats2bfloat162_rn(f[q + 4], f[q + 5]), a3 = __floats2bfloat162_rn(f[q + 6], f[q + 7]);
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(f[0], f[1]), a1 = __floats2bfloat162_rn(f[2], f[3]);
+              __nv_bfloat162 a2 = __floats2bfloat162_rn(f[4], f[5]), a3 = __floats2bfloat162_rn(f[6], f[7]);
               pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
               pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
-              *reinterpret_cast<uint4*>(o + q) = pk;
+              *reinterpret_cast<uint4*>(o) = pk;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) if (q < nco) o[q] = __float2bfloat16_rn(f[q]);
             }
           } else {
+            float* o = reinterpret_cast<float*>(p.out) + ((n * p.Cout + co0) * p.OH + oy) * p.OW + ox;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) if (q < nco) o[q] = __float2bfloat16_rn(f[q]);
+            for (int q = 0; q < 8; ++q) if (q < nco) o[(long long)q * p.OH * p.OW] = f[q];
           }
-        } else {
-          float* o = reinterpret_cast<float*>(p.out) + ((n * p.Cout + co0) * p.OH + oy) * p.OW + ox;
-#pragma unroll
-          for (int q = 0; q < 16; ++q) if (q < nco) o[(long long)q * p.OH * p.OW] = f[q];
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);           // 128 arrivals: the accumulator may be overwritten
     }
   }
   tc_fence_before();
@@ -321,7 +379,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 64);
         uint8_t* sa = smem + stage * STAGE_BYTES;
         mbar_expect_tx(&full_bar[stage], A_BYTES);
 #pragma unroll
@@ -336,7 +394,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_sleep(&full_bar[stage], phase, 20);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t sb = sa + A_BYTES;
@@ -355,8 +413,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
     const int t = threadIdx.x - 64;
     const int j = t & 7;
     const int rg = t >> 3;                   // rows rg + 16*i, i < 4
-    long long koff[NG];                      // element offset of this thread's k-chunk relative to the row's base pixel
-    int kdy[NG], kdx[NG];
+    int koff[NG];                            // element offset of this thread's k-chunk relative to the row's base pixel
     bool kval[NG];
 #pragma unroll
     for (int q = 0; q < NG; ++q) {
@@ -364,29 +421,29 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
       kval[q] = kidx < g.K;
       int a, b, c;
       decode_k(g, kidx, a, b, c);
-      kdy[q] = a * g.ts; kdx[q] = b * g.ts;
-      koff[q] = ((long long)kdy[q] * g.IW + kdx[q]) * g.C + c;
+      koff[q] = (a * g.IW + b) * g.C + c;    // gather geometry (ts = +1, no padding): every tap of a valid row lies inside the image
     }
     const int rhw = g.RH * g.RW;
     const uint32_t dst_off = (uint32_t)(rg * 128 + ((j ^ (rg & 7)) << 4));
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
+      mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
       const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES + A_BYTES) + dst_off;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long row = (long long)(kb_begin + kb) * CV_BK + rg + 16 * i;
+        int base = 0;
         const bool rok = row < g.rows;
-        long long n = 0; int yy = 0, xx = 0;
-        if (rok) decode_row(g, row, rhw, n, yy, xx);
-        const int iy0 = yy * g.sy, ix0 = xx * g.sy;
-        const __nv_bfloat16* base = g.in + ((n * g.IH + iy0) * g.IW + ix0) * g.C;
+        if (rok) {
+          long long n; int yy, xx;
+          decode_row(g, row, rhw, n, yy, xx);
+          base = (int)(((n * g.IH + yy * g.sy) * g.IW + xx * g.sy) * g.C);
+        }
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-          const bool ok = rok && kval[q] && (unsigned)(iy0 + kdy[q]) < (unsigned)g.IH && (unsigned)(ix0 + kdx[q]) < (unsigned)g.IW;
-          const void* src = ok ? (const void*)(base + koff[q]) : (const void*)g.in;
-          cp_async16(sb + q * 8192 + i * (16 * 128), src, ok ? 16u : 0u);
+          const bool ok = rok && kval[q];
+          cp_async16(sb + q * 8192 + i * (16 * 128), g.in + (ok ? base + koff[q] : 0), ok ? 16u : 0u);
         }
       }
       cp_async_commit();
@@ -402,7 +459,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
 
     // ------------------------------ epilogue: fp32 atomics into dW ------------------------------
     const int quarter = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait_sleep(tmem_full_bar, 0, 64);
     tc_fence_after();
     const int m = m0 + quarter * 32 + lane;
     const bool m_ok = m < p.Cs;
@@ -483,17 +540,31 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __re
 
 template <int BN>
 static int launch_fwd(const CUtensorMap& tw, const ConvFwdParams& p, cudaStream_t st) {
-  constexpr int STAGES = BN <= 96 ? 3 : 4;
+  constexpr int STAGES = FwdCfg<BN>::STAGES;
   constexpr int SMEM = STAGES * (CV_BM + BN) * CV_BK * 2 + 1024 + 256;
   static bool attr_set = false;
+  static int ctas_per_sm = 1, sms = 148;
   auto kern = conv_fwd_kernel<BN, STAGES>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     GENRL_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_fwd) failed: %s", cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    int occ = 0;
+    {
+      const int need = FwdCfg<BN>::CTAS * (SMEM + 1024);
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024)));
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CVF_THREADS, SMEM) != cudaSuccess) occ = -1;
+    ctas_per_sm = FwdCfg<BN>::CTAS;          // 2 CTAs x 2 accumulators of <= 128 TMEM columns fit the 512-column TMEM; smem 2 x 87 KB
+    if (getenv("GENRL_CONV_DEBUG")) fprintf(stderr, "conv_fwd<%d>: occupancy query %d, using %d CTAs/SM x %d SMs, smem %d\n", BN, occ, ctas_per_sm, sms, SMEM);
     attr_set = true;
   }
-  dim3 grid((unsigned)((p.g.rows + CV_BM - 1) / CV_BM), (unsigned)ceil_div(p.N, BN), 1);
-  kern<<<grid, CV_THREADS, SMEM, st>>>(tw, p);
+  const long long tiles = ((p.g.rows + CV_BM - 1) / CV_BM) * ceil_div(p.N, BN);
+  dim3 grid((unsigned)std::min<long long>(tiles, (long long)sms * ctas_per_sm), 1, 1);
+  kern<<<grid, CVF_THREADS, SMEM, st>>>(tw, p);
   return check_launch("conv_fwd_kernel");
 }
 
@@ -504,9 +575,10 @@ using namespace genrl;
 static int fill_geom(ConvGeom* g, const void* in, int Nimg, int IH, int IW, int C, int RH, int RW, int sy, int ts, int th, int tw) {
   GENRL_REQUIRE(C % 8 == 0 && C > 0, "conv_igemm: channels must be a multiple of 8 (got %d)", C);
   GENRL_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv_igemm: input must be 16-byte aligned");
-  GENRL_REQUIRE(IH < 4096 && IW < 4096 && RH * sy + th < 8192 && RW * sy + tw < 8192, "conv_igemm: image too large");
+  GENRL_REQUIRE(IH < 4096 && IW < 4096 && RH * sy + th < 8192 && RW * sy + tw < 8192 && th <= 8 && tw <= 8, "conv_igemm: image / filter too large");
+  GENRL_REQUIRE((long long)Nimg * IH * IW * C < (1LL << 31), "conv_igemm: input has more than 2^31 elements");
   g->in = reinterpret_cast<const __nv_bfloat16*>(in);
-  g->Nimg = Nimg; g->IH = IH; g->IW = IW; g->C = C; g->RH = RH; g->RW = RW; g->sy = sy; g->ts = ts; g->tw = tw;
+  g->Nimg = Nimg; g->IH = IH; g->IW = IW; g->C = C; g->RH = RH; g->RW = RW; g->sy = sy; g->ts = ts; g->th = th; g->tw = tw;
   g->K = th * tw * C;
   g->rows = (long long)Nimg * RH * RW;
   g->m_rhw = div_magic(g->rows, RH * RW);
@@ -526,13 +598,14 @@ extern "C" int genrl_conv_igemm_fwd(void* stream, const void* in, int Nimg, int 
   ConvFwdParams p;
   if (fill_geom(&p.g, in, Nimg, IH, IW, C, RH, RW, sy, ts, th, tw)) return 1;
   GENRL_REQUIRE(ncls == 1 || ncls == 4, "conv_igemm_fwd: ncls must be 1 or 4");
-  GENRL_REQUIRE(Cpad % 16 == 0 && Cout <= Cpad, "conv_igemm_fwd: Cpad must be a multiple of 16 covering Cout");
+  GENRL_REQUIRE(Cpad % 8 == 0 && Cout <= Cpad && (ncls * Cpad) % 16 == 0, "conv_igemm_fwd: Cpad must be a multiple of 8 covering Cout, N a multiple of 16");
   GENRL_REQUIRE(out_mode == 1 || Cout % 8 == 0, "conv_igemm_fwd: NHWC output needs Cout %% 8 == 0");
   GENRL_REQUIRE((ldw % 8) == 0 && (reinterpret_cast<uintptr_t>(Wm) & 15) == 0, "conv_igemm_fwd: filter matrix must be 16-byte aligned rows");
   p.N = ncls * Cpad; p.Cpad = Cpad; p.Cout = Cout; p.ncls = ncls; p.OH = OH; p.OW = OW; p.out_mode = out_mode; p.out = out; p.bias = bias;
   p.num_kb = ceil_div(p.g.K, CV_BK);
   int bn;
   if (p.N <= 16) bn = 16;
+  else if (p.N <= 32) bn = 32;
   else if (p.N <= 48) bn = 48;
   else if (p.N <= 64) bn = 64;
   else if (p.N <= 96) bn = 96;
@@ -542,6 +615,7 @@ extern "C" int genrl_conv_igemm_fwd(void* stream, const void* in, int Nimg, int 
   if (make_map(&tm, Wm, ncls == 1 ? Cout : p.N, p.g.K, ldw, 64, bn)) return 1;      // rows past the matrix are zero-filled by TMA
   switch (bn) {
     case 16: return launch_fwd<16>(tm, p, st);
+    case 32: return launch_fwd<32>(tm, p, st);
     case 48: return launch_fwd<48>(tm, p, st);
     case 64: return launch_fwd<64>(tm, p, st);
     case 96: return launch_fwd<96>(tm, p, st);
@@ -557,6 +631,7 @@ extern "C" int genrl_conv_igemm_wgrad(void* stream, const void* in, int Nimg, in
   if (Nimg <= 0) return 0;
   ConvWgParams p;
   if (fill_geom(&p.g, in, Nimg, IH, IW, C, RH, RW, sy, 1, th, tw)) return 1;
+  GENRL_REQUIRE((RH - 1) * sy + th <= IH && (RW - 1) * sy + tw <= IW, "conv_igemm_wgrad: taps must lie inside the image (gather geometry)");
   GENRL_REQUIRE((lds % 8) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0, "conv_igemm_wgrad: S must have 16-byte aligned rows");
   p.Cs = Cs; p.dw = dw; p.ldw = (int)lddw;
   p.num_kb = ceil_div(p.g.rows, CV_BK);

@@ -137,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait_sleep(tmem_full_bar, 0, 64);      // idle during the whole main loop: do not compete with the TMA / MMA lanes for issue slots
     tc_fence_after();
     const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < p.M;

@@ -739,7 +739,7 @@ def _igemm_gather(x, N, IH, IW, C, RH, RW, k, wm, ncols, bias, out=None):
 def _igemm_subpixel(x, N, IH, IW, C, OH, OW, k, w_master, A, B, bias, nchw=False):
     """out[n, oy, ox, b] = sum x[n, iy, ix, a] W4[a][b][oy-2iy][ox-2ix] (+bias): ConvTranspose2d fwd (W4 = its weight) / Conv2d dgrad"""
     T = (k + 1) // 2
-    Cpad = _pad16(B)
+    Cpad = _pad8(B)
     wq = torch.empty(4 * Cpad, T * T * A, device=x.device, dtype=torch.bfloat16)
     lib.genrl_conv_pack_parity(_st(), _p(w_master), _p(wq), A, B, k, Cpad)
     if nchw:
