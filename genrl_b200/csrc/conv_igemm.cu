@@ -538,6 +538,25 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __re
   }
 }
 
+// uint8 NCHW observation -> (x/255 - 0.5) bf16 NHWC with the channel dimension zero-padded to 8 (one 16-byte store per pixel):
+// the encoder's first layer then runs on the implicit-GEMM path like every other layer (preprocess dreamer.py:294-295 fused here)
+__global__ void __launch_bounds__(256) u8_nchw_to_nhwc8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ y, long long N, int C, int HW) {
+  const long long total = N * HW;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long n = i / HW;
+    const long long hw = i - n * HW;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? (float)x[(n * C + c) * HW + hw] / 255.0f - 0.5f : 0.f;
+    uint4 pk;
+    __nv_bfloat162 a0 = __floats2bfloat162_rn(v[0], v[1]), a1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 a2 = __floats2bfloat162_rn(v[4], v[5]), a3 = __floats2bfloat162_rn(v[6], v[7]);
+    pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+    pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+    y[i] = pk;
+  }
+}
+
 template <int BN>
 static int launch_fwd(const CUtensorMap& tw, const ConvFwdParams& p, cudaStream_t st) {
   constexpr int STAGES = FwdCfg<BN>::STAGES;
@@ -685,4 +704,12 @@ extern "C" int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, lon
   nchw_to_nhwc_pad_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, Cp);
   return check_launch("nchw_to_nhwc_pad");
+}
+
+extern "C" int genrl_u8_nchw_to_nhwc8(void* stream, const void* x, void* y, long long N, int C, int H, int W) {
+  GENRL_REQUIRE(C <= 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "u8_nchw_to_nhwc8: at most 8 channels, 16-byte aligned output");
+  const long long total = N * H * W;
+  u8_nchw_to_nhwc8_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint8_t*>(x), reinterpret_cast<uint4*>(y), N, C, H * W);
+  return check_launch("u8_nchw_to_nhwc8");
 }

@@ -120,6 +120,8 @@ int genrl_conv_pack_parity(void* stream, const float* w, void* dst, int A, int B
 int genrl_conv_pack_gather(void* stream, const float* w, void* dst, int A, int B, int k, int Cp);
 int genrl_conv_unpack_wgrad(void* stream, const float* dwp, long long ld, float* grad, int A, int B, int k, int Cp);
 int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, long long N, int C, int H, int W, int Cp);
+/* uint8 NCHW observation -> (x/255 - 0.5) bf16 NHWC, channels zero-padded to 8 (WorldModel.preprocess dreamer.py:294-295 + layout change). */
+int genrl_u8_nchw_to_nhwc8(void* stream, const void* x, void* y, long long N, int C, int H, int W);
 int genrl_permute_abp(void* stream, const void* src, int src_dtype, void* dst, int dst_dtype, long long A, int B, int P, int accumulate);
 
 /* Fused direct kernels for the 3-channel ends of the conv stacks (Encoder layer 0 + ImgChLayerNorm + SiLU, dreamer_utils.py:580-589;

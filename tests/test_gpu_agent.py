@@ -172,3 +172,32 @@ def test_overlapped_streams_match_single_stream():
         assert all(np.isfinite(v) for v in h.values())
     assert b[3]["model_loss"] < b[0]["model_loss"]
     ops.set_noise(ops.PhiloxNoise(0))
+
+
+def test_kitchen_shaped_agent_full_conv_stack_bf16_tracks_fp32():
+    """BASELINE configs[3]: kitchen has A = 9 and an extra low-dimensional `state` observation key that the GenRL encoder ignores
+    (conf/env/dmc_pixels.yaml: mlp_keys '$^').  Full-size conv stacks (depth 48, 64x64), small batch: the bf16 tensor-core path
+    (implicit-GEMM convolutions) must track the fp32 parity path of the same weights on the same draws."""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from genrl_b200.config import Spec
+    from genrl_b200.synthetic import synthetic_batch
+    B, T, A, H = 3, 16, 9, 4
+    results = {}
+    for precision in (32, 16):
+        cfg = genrl_config(device=DEV, precision=precision, batch_size=B, batch_length=T, imag_horizon=H)
+        obs_space, act_spec = make_specs(action_dim=A, clip_dim=512)
+        obs_space["state"] = Spec((30,), "float32")
+        torch.manual_seed(1)
+        agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+        data = {k: v.to(DEV) for k, v in synthetic_batch(B, T, A, clip_dim=512, seed=3, resets=0.1).items()}
+        data["state"] = torch.zeros(B, T, 30, device=DEV)
+        ops.set_noise(ops.PhiloxNoise(7))
+        state, outputs, metrics = agent.update_wm(data, 0)
+        start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+        assert outputs["embed"].shape == (B, T, 1536) and outputs["post"]["stoch"].shape == (B, T, 32, 32)
+        results[precision] = {k: float(torch.as_tensor(v).float().cpu().reshape(-1)[0]) for k, v in metrics.items()}
+        assert all(np.isfinite(v) for v in results[precision].values())
+    for k in ("observation_loss", "reward_loss", "kl_loss", "model_loss", "connector_model_loss"):
+        a, b = results[16][k], results[32][k]
+        assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), f"{k}: bf16 {a} vs fp32 {b}"
