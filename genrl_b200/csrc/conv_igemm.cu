@@ -122,7 +122,7 @@ template <int STAGES> struct DrainStages<0, STAGES> {
 };
 
 // shared-memory stages of the forward kernel.  The L1 that is left over matters: every input pixel is re-read by 4..9 taps, and
-// the 5/6-stage variants measured 20-30 % slower on the wide tiles than 4 stages (profiles/r01_conv_notes.md)
+// the 5/6-stage variants measured 20-30 % slower on the wide tiles than 4 stages (profiles/r01_notes.md §3)
 template <int BN> struct FwdCfg {
   static constexpr int STAGES = BN <= 96 ? 3 : 4;      // measured: deeper rings do not help (the gather is not latency bound) and cost L1 capacity
   static constexpr int LAG = STAGES - 1;

@@ -322,7 +322,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// Tile policy, from measurements on B200 (tests/tune_gemm.py, profiles/r01_gemm_by_shape.txt, ncu --set full in profiles/):
+// Tile policy, from measurements on B200 (tests/tune_gemm.py, profiles/r01_kineto_step_bf16.txt "GEMM by shape", profiles/r01_notes.md):
 // at the sizes of this path the kernel is bound by operand-feed LATENCY (a 16..38-deep K loop fed from L2/HBM), not by the tensor
 // pipe or by bandwidth, so what matters is bytes in flight per SM: 128x128 tiles with two co-resident CTAs per SM (2 x 3 stages,
 // and one CTA's prologue/epilogue hidden behind the other's main loop) beat wider single-CTA tiles by 2-3x on cold operands.

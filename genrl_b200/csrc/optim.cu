@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, long 
 // state[0] = step count (as float), state[1] = grad norm of the last call (metric)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    long long n, float lr, float eps, float clip, const float* __restrict__ sumsq,
-                                                   const float* __restrict__ state) {
+                                                   const float* __restrict__ state, float decay) {
   const float norm = sqrtf(*sumsq);
   const float coef = clip > 0.f ? fminf(clip / (norm + 1e-6f), 1.0f) : 1.0f;
   const float t = state[0] + 1.0f;
@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     float vi = v[i] * 0.999f + gi * gi * (1.0f - 0.999f);
     m[i] = mi; v[i] = vi;
     float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    const float pi = decay != 1.0f ? __fmul_rn(p[i], decay) : p[i];     // multiplicative weight decay first (dreamer_utils.py:926-932), own rounding
+    p[i] = pi - step_size * (mi / denom);
     g[i] = 0.f;
   }
 }
@@ -209,8 +210,8 @@ extern "C" int genrl_scale(void* stream, float* p, long long n, float s) {
 // p,g,m,v: flat fp32 [n]; sumsq: device scalar from genrl_grad_sumsq (norm over the whole optimizer call);
 // state: device float[2] {step, last grad norm}; `finish` bumps the step (set on the last segment of a call).
 extern "C" int genrl_adam_step(void* stream, float* p, float* g, float* m, float* v, long long n, float lr, float eps, float clip,
-                               const float* sumsq, float* state, int finish) {
-  if (n > 0) adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, eps, clip, sumsq, state);
+                               const float* sumsq, float* state, int finish, float decay) {
+  if (n > 0) adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, eps, clip, sumsq, state, decay);
   if (finish) adam_finish_kernel<<<1, 1, 0, ST(stream)>>>(state, sumsq);
   return check_launch("adam_step");
 }

@@ -149,13 +149,15 @@ class ParamStore:
             first = False
         if first:
             self.sumsq.zero_()
+        decay = 1.0 - wd if wd else 1.0
         if wd:
             for g in groups:
-                lib.genrl_scale(st, g.flat.data_ptr(), g.numel, 1.0 - wd)
+                if not any(g is a for a in active):       # groups without gradients still decay (reference :926-932 runs on every param)
+                    lib.genrl_scale(st, g.flat.data_ptr(), g.numel, decay)
         norm = None
-        for g in active:
+        for g in active:                                   # decay folded into the Adam pass: p <- p*(1-wd), then the Adam update
             lib.genrl_adam_step(st, g.flat.data_ptr(), g.grad.data_ptr(), g.m.data_ptr(), g.v.data_ptr(), g.numel, lr, eps,
-                                float(clip or 0.0), self.sumsq.data_ptr(), g.state.data_ptr(), 1)
+                                float(clip or 0.0), self.sumsq.data_ptr(), g.state.data_ptr(), 1, decay)
             g.touched = False
             norm = g.state[1]
         for g in groups:

@@ -141,7 +141,7 @@ int genrl_convT3_mse_bwd(void* stream, const void* x, const float* w, const floa
 int genrl_grad_sumsq(void* stream, const float* g, long long n, float* sumsq_out, int zero_first);
 int genrl_scale(void* stream, float* p, long long n, float s);
 int genrl_adam_step(void* stream, float* p, float* g, float* m, float* v, long long n, float lr, float eps, float clip, const float* sumsq,
-                    float* state, int finish);
+                    float* state, int finish, float decay);
 int genrl_pack_weights(void* stream, const void* table, int n_entries, int dst_dtype);
 int genrl_pack_entry_size();
 
