@@ -27,6 +27,13 @@ int genrl_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* sm
 int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W, long long ldw, int transW,
                int in_dtype, void* C, long long ldc, int c_dtype, const float* bias, int accumulate);
 
+/* Linear + LayerNorm(+SiLU) fused (bf16, N multiple of 128 up to 1024): the N/128 column-tile CTAs of a row stripe form a thread-block
+ * cluster and merge their per-row (mean, M2) partials through distributed shared memory.  Replaces Linear -> NormLayer -> act
+ * (dreamer_utils.py:738-744, :339-346).  pre is kept for the backward pass; stats[M][2] = (mean, rstd). */
+int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, const float* bias,
+                      const float* gamma, const float* beta, float eps, int act, void* pre, long long ldpre, void* y, long long ldy,
+                      float* stats);
+
 /* LayerNorm(+SiLU) rows: NormLayer dreamer_utils.py:844-859 / ImgChLayerNorm :1031-1040 + act (:744, :589). */
 int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act, void* y,
                      long long ldy, float* stats, long long M, int D, int dtype);
