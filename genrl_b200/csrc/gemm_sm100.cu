@@ -242,8 +242,10 @@ struct LnParams {
   float* stats;                 // [M][2] mean, rstd
 };
 
+constexpr int LN_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 64 columns each)
+
 template <int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(LN_THREADS, 2)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LnParams p) {
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
@@ -255,7 +257,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float2* row_part = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);      // [128] (mean, M2) of this CTA's column slice
+  float2* row_part = reinterpret_cast<float2*>(smem + STAGES * STAGE_BYTES + 256);      // [2][128] (sum, sum of squares) per column half
+  float* s_bias = reinterpret_cast<float*>(row_part + 256);                             // [128] each: bias, gamma, beta of this CTA's columns
+  float* s_gamma = s_bias + BN;
+  float* s_beta = s_gamma + BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -278,15 +283,21 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {          // stage the column parameters while the main loop runs
+    const int c = threadIdx.x - 64;
+    s_bias[c] = p.bias ? p.bias[n0 + c] : 0.f;
+    s_gamma[c] = p.gamma[n0 + c];
+    s_beta[c] = p.beta[n0 + c];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  float mean_l = 0.f;
-  const int quarter = warp & 3;
+  const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+  const int half = warp >= 6 ? 1 : 0;           // warps 2..5: columns 0..63, warps 6..9: columns 64..127
   const int r = quarter * 32 + lane;            // row of the tile owned by an epilogue thread
-  const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -320,56 +331,52 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ---- epilogue part A: local statistics of this CTA's 128 columns ----
+    // ---- epilogue part A: (sum, sum of squares) of this thread's 64 columns ----
     mbar_wait_sleep(tmem_full_bar, 0, 64);
     tc_fence_after();
-    float s = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(trow + (uint32_t)c, v);
+    float s = 0.f, ss = 0.f;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) s += __uint_as_float(v[q]) + (p.bias ? __ldg(p.bias + n0 + c + q) : 0.f);
-    }
-    mean_l = s * (1.0f / BN);
-    float m2 = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
       uint32_t v[32];
-      tmem_ld32(trow + (uint32_t)c, v);
+      tmem_ld32(tcol + (uint32_t)c, v);
 #pragma unroll
-      for (int q = 0; q < 32; ++q) { const float d = __uint_as_float(v[q]) + (p.bias ? __ldg(p.bias + n0 + c + q) : 0.f) - mean_l; m2 += d * d; }
+      for (int q = 0; q < 32; ++q) { const float x = __uint_as_float(v[q]) + s_bias[half * 64 + c + q]; s += x; ss = fmaf(x, x, ss); }
     }
-    row_part[r] = make_float2(mean_l, m2);
+    row_part[half * 128 + r] = make_float2(s, ss);
   }
   __syncwarp();
   cluster_sync_all();                            // every CTA of the stripe has published its row partials
   if (warp >= 2) {
     // ---- epilogue part B: merge the partials over the cluster, normalise, activate, store ----
-    float msum = 0.f;
-    for (int q = 0; q < ncta; ++q) msum += ld_dsmem_f2(&row_part[r], (uint32_t)q).x;
-    const float mean = msum / ncta;
-    float M2 = 0.f;
-    for (int q = 0; q < ncta; ++q) { const float2 t = ld_dsmem_f2(&row_part[r], (uint32_t)q); const float d = t.x - mean; M2 += t.y + BN * d * d; }
-    const float rstd = 1.0f / sqrtf(M2 / p.N + p.eps);
+    float2 t0[8], t1[8];                          // all remote loads in flight together (~215 cycles each), then the sums
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t src = q < ncta ? (uint32_t)q : 0u;
+      t0[q] = ld_dsmem_f2(&row_part[r], src); t1[q] = ld_dsmem_f2(&row_part[128 + r], src);
+    }
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) if (q < ncta) { s += t0[q].x + t1[q].x; ss += t0[q].y + t1[q].y; }
+    const float mean = s / p.N;
+    const float rstd = 1.0f / sqrtf(fmaxf(ss / p.N - mean * mean, 0.f) + p.eps);
     const int row = m0 + r;
     const bool row_ok = row < p.M;
-    if (row_ok && n0 == 0) { p.stats[(size_t)row * 2] = mean; p.stats[(size_t)row * 2 + 1] = rstd; }
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    if (row_ok && n0 == 0 && half == 0) { p.stats[(size_t)row * 2] = mean; p.stats[(size_t)row * 2 + 1] = rstd; }
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
       uint32_t v[32];
-      tmem_ld32(trow + (uint32_t)c, v);
+      tmem_ld32(tcol + (uint32_t)c, v);
       if (!row_ok) continue;
-      __nv_bfloat16* po = p.pre + (size_t)row * p.ldpre + n0 + c;
-      __nv_bfloat16* yo = p.y + (size_t)row * p.ldy + n0 + c;
+      const int cc = half * 64 + c;
+      __nv_bfloat16* po = p.pre + (size_t)row * p.ldpre + n0 + cc;
+      __nv_bfloat16* yo = p.y + (size_t)row * p.ldy + n0 + cc;
 #pragma unroll
       for (int q = 0; q < 32; q += 8) {
         float x[8], o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int col = n0 + c + q + e;
-          x[e] = __uint_as_float(v[q + e]) + (p.bias ? __ldg(p.bias + col) : 0.f);
-          const float a = (x[e] - mean) * rstd * __ldg(p.gamma + col) + __ldg(p.beta + col);
+          x[e] = __uint_as_float(v[q + e]) + s_bias[cc + q + e];
+          const float a = (x[e] - mean) * rstd * s_gamma[cc + q + e] + s_beta[cc + q + e];
           o[e] = p.act == GENRL_ACT_SILU ? silu_t<true>(a) : a;
         }
         uint4 pk, yk;
@@ -611,7 +618,7 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   p.pre = reinterpret_cast<__nv_bfloat16*>(pre); p.ldpre = (int)ldpre;
   p.y = reinterpret_cast<__nv_bfloat16*>(y); p.ldy = (int)ldy; p.stats = stats;
   constexpr int STAGES = 3;
-  constexpr int SMEM = STAGES * (TC_BM + 128) * TC_BK * 2 + 1024 + 256 + 1024;
+  constexpr int SMEM = STAGES * (TC_BM + 128) * TC_BK * 2 + 1024 + 256 + 2048 + 1536;
   auto kern = gemm_ln_kernel<STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -621,7 +628,7 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(N / 128, ceil_div(M, TC_BM), 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3(LN_THREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
