@@ -210,6 +210,180 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // =================================================================================================
+// Persistent 256x128 GEMM for the large-M shapes (the 36 000 / 38 400-row head and critic GEMMs: 60 % of the step's GEMM FLOPs).
+// The 128x128 kernel above is bound by per-SM operand ingest there (two co-resident CTAs pull 64 KB from L2 per 4.2 MFLOP, measured
+// ~90 GB/s per SM -> 800-870 TFLOP/s).  Here one CTA per SM computes a 256-row tile with TWO UMMA_M=128 instructions per k-step that
+// share the B tile (48 KB per 4.2 MFLOP), walks tiles persistently, and double-buffers the 2x128-column accumulator pair in TMEM
+// (2 x 256 of the 512 columns) so the 8 epilogue warps drain tile i while TMA/MMA already run tile i+1.
+// A is K-major; B is K-major (forward) or MN-major (dgrad).  Plain stores only (no split-K, no accumulate).
+// =================================================================================================
+constexpr int PG_BM = 256;
+constexpr int PG_BN = 128;
+constexpr int PG_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps (rows 0..127: warps 2..5, rows 128..255: warps 6..9)
+constexpr int PG_STAGES = 4;
+
+template <bool B_MN>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = PG_BM * TC_BK * 2;          // 32 KB: rows 0..127 at +0, rows 128..255 at +16 KB
+  constexpr int B_BYTES = PG_BN * TC_BK * 2;          // 16 KB
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PG_STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + PG_STAGES;
+  uint64_t* tfull_bar = empty_bar + PG_STAGES;        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = p.num_kb;
+  const int tiles_n = (p.N + PG_BN - 1) / PG_BN;
+  const int tiles = ((p.M + PG_BM - 1) / PG_BM) * tiles_n;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < PG_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * PG_BM, n0 = (t % tiles_n) * PG_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sa, kb * TC_BK, m0);                          // box {64 k, 256 m}
+          if (!B_MN) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * TC_BK, n0);                        // box {64 k, 128 n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < PG_BN / 64; ++j)                                            // box {64 n, 64 k}
+              tma_load_2d(&tmB, &full_bar[stage], sb + j * (64 * TC_BK * 2), n0 + 64 * j, kb * TC_BK);
+          }
+          if (++stage == PG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(PG_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait_sleep(&tempty_bar[buf], ((it >> 1) & 1) ^ 1, 32);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 64 * TC_BK * 2, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16(acc, make_smem_desc(sa + k * 32, 16, 1024), bd, idesc, accum);                       // rows 0..127
+            umma_bf16(acc + 128, make_smem_desc(sa + 128 * TC_BK * 2 + k * 32, 16, 1024), bd, idesc, accum); // rows 128..255
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull_bar[buf]);
+          if (++stage == PG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (warps 2..9) ------------------------------
+    const int quarter = warp & 3;
+    const int half = warp >= 6 ? 1 : 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m0 = (t / tiles_n) * PG_BM, n0 = (t % tiles_n) * PG_BN;
+      mbar_wait_sleep(&tfull_bar[buf], (it >> 1) & 1, 64);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 256 + half * 128) + ((uint32_t)(quarter * 32) << 16);
+      const int row = m0 + half * 128 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < PG_BN; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(acc + (uint32_t)c, v);
+        if (!row_ok) continue;
+        const int col0 = n0 + c;
+        const int ncols = min(32, p.N - col0);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (p.c_dtype == GENRL_F32) {
+          float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = f[j];
+          }
+        } else {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
+          if (ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 a0 = __floats2bfloat162_rn(f[j], f[j + 1]), a1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 a2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]), a3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+              pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+              *reinterpret_cast<uint4*>(out + j) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_local(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// =================================================================================================
 // Linear + LayerNorm (+SiLU) in one kernel:  pre = A W^T + b ;  y = act(LN(pre))           (N = 128 .. 1024, multiple of 128)
 // The N/128 CTAs that own the column tiles of one 128-row stripe form a thread-block CLUSTER.  Each epilogue thread owns one row of
 // its CTA's 128 fp32 accumulator columns in TMEM, computes the local (mean, M2) of that row slice, publishes it in shared memory,
@@ -574,6 +748,34 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
   GENRL_REQUIRE(!(accumulate && c_dtype != GENRL_F32), "genrl_gemm: accumulate needs fp32 C");
   GENRL_REQUIRE((lda % 8) == 0 && (ldw % 8) == 0, "genrl_gemm: bf16 leading dimensions must be multiples of 8 (lda=%lld ldw=%lld)", lda, ldw);
   GENRL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "genrl_gemm: operands must be 16B aligned");
+  // large-M forward / dgrad shapes: persistent 256x128 kernel (see gemm_tc_persist_kernel)
+  // GENRL_GEMM_PERSIST: 0 = never, 2 = whenever the kernel supports the call (tests), default = large-M shapes only
+  const char* pm = getenv("GENRL_GEMM_PERSIST");
+  const int persist_mode = pm ? atoi(pm) : 1;
+  const bool persist_ok = !transA && !accumulate;
+  // measured (tests/debug_pgemm.py): 1.02-1.15 PFLOP/s vs 0.79-1.0 for N >= 1024; N = 255 (300 tiles = 2.03 waves) loses to the 128x128 kernel
+  const bool persist_auto = M >= 8192 && N >= 512 && (long long)ceil_div(M, PG_BM) * ceil_div(N, PG_BN) >= 4 * num_sms();
+  if (persist_ok && (persist_mode == 2 || (persist_mode == 1 && persist_auto))) {
+    CUtensorMap pa, pb;
+    if (make_map(&pa, A, M, K, lda, 64, PG_BM)) return 1;
+    if (!transW) { if (make_map(&pb, W, N, K, ldw, 64, PG_BN)) return 1; }
+    else         { if (make_map(&pb, W, K, N, ldw, 64, 64)) return 1; }
+    TcParams q;
+    q.M = M; q.N = N; q.K = K; q.ldc = (int)ldc; q.c_dtype = c_dtype; q.accumulate = 0; q.atomic = 0;
+    q.num_kb = ceil_div(K, TC_BK); q.kb_per_split = q.num_kb; q.bias = bias; q.C = C;
+    constexpr int SMEM = PG_STAGES * (PG_BM + PG_BN) * TC_BK * 2 + 1024 + 256;
+    static bool attr_set[2] = {false, false};
+    const int tiles = ceil_div(M, PG_BM) * ceil_div(N, PG_BN);
+    const int grid = std::min(tiles, num_sms());
+    if (!transW) {
+      if (!attr_set[0]) { cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set[0] = true; }
+      gemm_tc_persist_kernel<false><<<grid, PG_THREADS, SMEM, st>>>(pa, pb, q);
+    } else {
+      if (!attr_set[1]) { cudaFuncSetAttribute(gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set[1] = true; }
+      gemm_tc_persist_kernel<true><<<grid, PG_THREADS, SMEM, st>>>(pa, pb, q);
+    }
+    return check_launch("gemm_tc_persist_kernel");
+  }
   int bn, splits;
   choose_tiling(M, N, K, c_dtype == GENRL_F32, transW != 0, &bn, &splits);
   CUtensorMap ta, tb;

@@ -68,6 +68,22 @@ def test_gemm_bf16_tcgen05(ta, tw, M, N, K):
     close(acc, a.float() @ w.float().t() + 0.5, rtol=2e-5, atol=1e-4, msg="tcgen05 gemm accumulate")
 
 
+@pytest.mark.parametrize("tw", [False, True])
+@pytest.mark.parametrize("M,N,K", [(700, 255, 136), (1000, 384, 1024), (38400, 1024, 1024), (36000, 255, 1024)])
+def test_gemm_bf16_persistent_256x128(tw, M, N, K, monkeypatch):
+    """persistent 256x128 kernel (two UMMA per k-step sharing the B tile, double-buffered TMEM): forced on small shapes too"""
+    monkeypatch.setenv("GENRL_GEMM_PERSIST", "2")
+    a = rnd(M, K).to(torch.bfloat16)
+    w = rnd(N, K, seed=1).to(torch.bfloat16)
+    b = rnd(N, seed=2)
+    ad = ops.cast_to(a.to(DEV), torch.bfloat16)
+    wd = ops.cast_to((w.t().contiguous() if tw else w).to(DEV), torch.bfloat16)
+    ref = ad.float() @ w.to(DEV).float().t() + b.to(DEV)
+    for out_dtype in (torch.bfloat16, torch.float32):
+        out = ops.gemm(ad, wd, bias=b.to(DEV), trans_w=tw, out_dtype=out_dtype)
+        close(out, ref, rtol=2e-2 if out_dtype == torch.bfloat16 else 2e-3, atol=1e-2, msg=f"persistent gemm {out_dtype}")
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,D,eps,act", [(37, 64, 1e-5, 1), (1000, 1024, 1e-5, 1), (333, 48, 1e-3, 1), (50, 3072, 1e-5, 0)])
 def test_ln_act(dtype, M, D, eps, act):
