@@ -64,21 +64,24 @@ __device__ __forceinline__ float silu_gradf_(float x) {
 }
 
 // bf16 mode uses the SFU fast paths (ex2/rcp approximations, ~2 ulp): activations are rounded to bf16 right after anyway.
-// (MUFU.EX2 + MUFU.RCP / MUFU.TANH as single instructions: the IEEE __frcp_rn / non-ftz __expf forms cost a slow-path branch per element,
-// which made the row kernels instruction-issue bound)
-__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// One MUFU per activation: sigmoid(x) = 0.5 + 0.5 tanh(x/2) with tanh.approx.f32 (rel. error 2^-11, abs. error of the sigmoid <= 2.5e-4,
+// below the bf16 rounding of the O(1) activations stored next).  The IEEE forms (__frcp_rn: slow-path call per element; ex2 + rcp: two
+// MUFU + two FP ops) made the row kernels instruction-issue / MUFU bound (profiles/r01_notes.md §2).
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <bool FAST> __device__ __forceinline__ float sigm_t(float x) {
-  if (FAST) return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * x));
+  if (FAST) return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f);
   return 1.0f / (1.0f + expf(-x));
 }
-template <bool FAST> __device__ __forceinline__ float silu_t(float x) { return x * sigm_t<FAST>(x); }
+template <bool FAST> __device__ __forceinline__ float silu_t(float x) {
+  if (FAST) { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+  return x * sigm_t<FAST>(x);
+}
 template <bool FAST> __device__ __forceinline__ float silu_grad_t(float x) {
   float s = sigm_t<FAST>(x);
   return s * (1.0f + x * (1.0f - s));
 }
 template <bool FAST> __device__ __forceinline__ float tanh_t(float x) {
-  if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+  if (FAST) return tanh_fast(x);
   return tanhf(x);
 }
 

@@ -52,7 +52,7 @@ __device__ __forceinline__ float group_sum(float v, int lpr) {
 // NCH = chunks (of 8 elements) per lane: 4 for wide rows (up to 32*4*8 = 1024), 6 for the narrow conv rows (48..384 channels,
 // 1..8 lanes per row: more rows per warp and more bytes in flight per lane)
 template <typename T, int FAST_NCH>
-__global__ void __launch_bounds__(256) ln_fwd_fast_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, (FAST_NCH == 4 ? 4 : 2)) ln_fwd_fast_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, int act, T* __restrict__ y, long long ldy,
                                                           float* __restrict__ stats, long long M, int D, int lpr) {
   const int lane = threadIdx.x & 31, sub = lane % lpr, rwi = lane / lpr, rpw = 32 / lpr;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) ln_fwd_fast_kernel(const T* __restrict__ 
 
 // ---- LayerNorm (+SiLU) backward, row pass: dx only ------------------------------------------------------------------
 template <typename T, int FAST_NCH>
-__global__ void __launch_bounds__(256) ln_bwd_fast_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
+__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
                                                           long long M, int D, int lpr) {
