@@ -201,3 +201,33 @@ def test_kitchen_shaped_agent_full_conv_stack_bf16_tracks_fp32():
     for k in ("observation_loss", "reward_loss", "kl_loss", "model_loss", "connector_model_loss"):
         a, b = results[16][k], results[32][k]
         assert abs(a - b) <= 2e-2 * max(1.0, abs(b)), f"{k}: bf16 {a} vs fp32 {b}"
+
+
+def test_ragged_shapes_resets_and_graph_replay_bf16():
+    """odd batch / action sizes, frequent is_first resets, short horizon; eager and CUDA-graph replays give the same losses"""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from genrl_b200.config import tiny_overrides
+    from genrl_b200.synthetic import synthetic_batch
+    B, T, A, H = 5, 24, 7, 3
+    losses = {}
+    for graph in (False, True):
+        cfg = genrl_config(device=DEV, precision=16, batch_size=B, batch_length=T, imag_horizon=H, **tiny_overrides())
+        cfg.cuda_graph = graph
+        obs_space, act_spec = make_specs(action_dim=A, clip_dim=32)
+        torch.manual_seed(1)
+        agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+        ops.set_noise(ops.PhiloxNoise(11))
+        out = []
+        for i in range(4):
+            data = {k: v.to(DEV) for k, v in synthetic_batch(B, T, A, clip_dim=32, seed=20 + i, resets=0.3).items()}
+            state, outputs, metrics = agent.update_wm(data, i)
+            start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+            out.append([float(metrics[k]) for k in ("model_loss", "connector_model_loss", "actor_loss", "critic_loss")])
+            assert all(np.isfinite(v) for v in out[-1]), (graph, i, out[-1])
+            assert outputs["post"]["stoch"].shape == (B, T) + tuple(outputs["post"]["stoch"].shape[2:])
+        losses[graph] = out
+    # calls 0-1 are eager in both runs; the captured replays (calls 2-3) must reproduce the eager numbers of the same step
+    for a, b in zip(losses[False], losses[True]):
+        for x, y in zip(a, b):
+            assert abs(x - y) <= 2e-2 * max(1.0, abs(x)), (losses[False], losses[True])
