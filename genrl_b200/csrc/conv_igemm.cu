@@ -137,8 +137,10 @@ template <int BN> struct FwdCfg {
 // =================================================================================================
 constexpr int CVF_THREADS = 448;     // TMA warp, MMA warp, 8 gather warps, 4 epilogue warps
 
+// Registers are allocated per 4 warps: a 448-thread CTA occupies 16 warp slots, so two CTAs per SM need <= 64 registers per thread
+// (tools/occ_probe.cu; __launch_bounds__(448, 2) alone lets ptxas use 72 and silently drops to one CTA per SM).
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(CVF_THREADS, (BN <= 96 ? 2 : 1))
+__global__ void __launch_bounds__(CVF_THREADS) __maxnreg__(BN <= 96 ? 64 : 128)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

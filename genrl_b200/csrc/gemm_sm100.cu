@@ -418,8 +418,9 @@ struct LnParams {
 
 constexpr int LN_THREADS = 320;     // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter, 64 columns each)
 
+// 320 threads = 10 warps occupy 12 warp slots of the register file (allocation granularity 4 warps): two CTAs per SM need <= 85 registers
 template <int STAGES>
-__global__ void __launch_bounds__(LN_THREADS, 2)
+__global__ void __maxnreg__(80)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LnParams p) {
   constexpr int BN = 128;
   extern __shared__ uint8_t smem_raw[];
@@ -826,6 +827,9 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     GENRL_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_ln) failed: %s", cudaGetErrorString(e));
+    // cluster launches are admitted by the occupancy the driver computes for the *current* carve-out: ask for the shared-memory-heavy
+    // split explicitly, otherwise only one CTA per SM (15 clusters of 8) is co-scheduled and a 19-cluster grid takes two waves
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -837,6 +841,12 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = N / 128; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (getenv("GENRL_GEMM_DEBUG")) {
+    int ncl = -1;
+    cudaError_t eo = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+    fprintf(stderr, "gemm_ln_fwd: M=%d N=%d K=%d cluster=%d grid=(%d,%d) max active clusters %d (%s)\n", M, N, K, N / 128, N / 128, ceil_div(M, TC_BM), ncl,
+            cudaGetErrorString(eo));
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
   GENRL_REQUIRE(e == cudaSuccess, "gemm_ln_fwd launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_ln_kernel");
