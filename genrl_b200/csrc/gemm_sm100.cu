@@ -690,7 +690,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// Tile policy, from measurements on B200 (tests/tune_gemm.py, profiles/r01_kineto_step_bf16.txt "GEMM by shape", profiles/r01_notes.md):
+// Tile policy, from measurements on B200 (tools/tune_gemm.py, profiles/r01_kineto_step_bf16.txt "GEMM by shape", profiles/r01_notes.md):
 // at the sizes of this path the kernel is bound by operand-feed LATENCY (a 16..38-deep K loop fed from L2/HBM), not by the tensor
 // pipe or by bandwidth, so what matters is bytes in flight per SM: 128x128 tiles with two co-resident CTAs per SM (2 x 3 stages,
 // and one CTA's prologue/epilogue hidden behind the other's main loop) beat wider single-CTA tiles by 2-3x on cold operands.
@@ -709,7 +709,7 @@ static void choose_tiling(int M, int N, int K, bool allow_split, bool b_mn, int*
   int best_bn = bn, best_s = sp;
   *bn_out = best_bn;
   *splits_out = best_s;
-  // tuning hook (tests/tune_gemm.py): GENRL_GEMM_BN / GENRL_GEMM_SPLITS force a configuration
+  // tuning hook (tools/tune_gemm.py): GENRL_GEMM_BN / GENRL_GEMM_SPLITS force a configuration
   static const char* fb = getenv("GENRL_GEMM_FORCE");
   if (fb) {
     const char* e1 = getenv("GENRL_GEMM_BN"); const char* e2 = getenv("GENRL_GEMM_SPLITS");
@@ -754,7 +754,7 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
   const char* pm = getenv("GENRL_GEMM_PERSIST");
   const int persist_mode = pm ? atoi(pm) : 1;
   const bool persist_ok = !transA && !accumulate;
-  // measured (tests/debug_pgemm.py): 1.02-1.15 PFLOP/s vs 0.79-1.0 for N >= 1024; N = 255 (300 tiles = 2.03 waves) loses to the 128x128 kernel
+  // measured (tools/debug_pgemm.py): 1.02-1.15 PFLOP/s vs 0.79-1.0 for N >= 1024; N = 255 (300 tiles = 2.03 waves) loses to the 128x128 kernel
   const bool persist_auto = M >= 8192 && N >= 512 && (long long)ceil_div(M, PG_BM) * ceil_div(N, PG_BN) >= 4 * num_sms();
   if (persist_ok && (persist_mode == 2 || (persist_mode == 1 && persist_auto))) {
     CUtensorMap pa, pb;

@@ -354,7 +354,7 @@ def ln_act(x, gamma, beta, eps=1e-5, act=ACT_SILU):
     return _LnAct.apply(x, gamma, beta, eps, act)
 
 
-# Widest layer that takes the cluster-fused Linear+LayerNorm kernel.  Measured on B200 (tests/debug_fused_ln.py, 20 layers in a CUDA
+# Widest layer that takes the cluster-fused Linear+LayerNorm kernel.  Measured on B200 (tools/debug_fused_ln.py, 20 layers in a CUDA
 # graph): N = 128 / 512 fused 10.5 / 13.9 us vs 12.7 / 15.9 us unfused; at N = 1024 (cluster of 8) the un-overlapped epilogue + two
 # cluster barriers cost as much as the separate LayerNorm launch (20.2 vs 19.5 us), so the 1024-wide layers stay on the two-kernel path.
 FUSED_LN_MAX_N = 512

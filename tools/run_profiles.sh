@@ -5,10 +5,10 @@
 #  3. ncu --set full of the persistent RSSM scan kernels, raw page exported as CSV
 mkdir -p gpurun_out
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-    --log-file gpurun_out/launches_step.csv python tests/ncu_step.py 16 > gpurun_out/ncu_step.log 2>&1
-python tests/summarize_launches.py gpurun_out/launches_step.csv gpurun_out/gemm_traffic.json > gpurun_out/launches_summary.txt 2>&1
+    --log-file gpurun_out/launches_step.csv python tools/ncu_step.py 16 > gpurun_out/ncu_step.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_step.csv gpurun_out/gemm_traffic.json > gpurun_out/launches_summary.txt 2>&1
 timeout 600 ncu --profile-from-start off --set full --clock-control none -k regex:rssm_scan -c 4 -f -o gpurun_out/scan_full \
-    python tests/ncu_step.py 16 > gpurun_out/ncu_scan.log 2>&1
+    python tools/ncu_step.py 16 > gpurun_out/ncu_scan.log 2>&1
 ncu -i gpurun_out/scan_full.ncu-rep --page raw --csv > gpurun_out/scan_full_raw.csv 2>> gpurun_out/ncu_scan.log
 rm -f gpurun_out/scan_full.ncu-rep
 cat gpurun_out/launches_summary.txt | head -30
