@@ -851,3 +851,22 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   GENRL_REQUIRE(e == cudaSuccess, "gemm_ln_fwd launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_ln_kernel");
 }
+
+// Debug aid: function attributes and the occupancy the runtime computes for the tensor-core kernels (printed to stderr).
+template <typename K> static void dbg_occ(const char* name, K kern, int threads, int smem) {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, kern);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int occ = -1;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+  fprintf(stderr, "%-28s regs %3d static smem %5zu local %4zu maxThreads %4d | threads %d dyn smem %6d -> blocks/SM %d (%s)\n", name, fa.numRegs,
+          fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock, threads, smem, occ, cudaGetErrorString(e));
+}
+extern "C" int genrl_debug_occupancy() {
+  dbg_occ("gemm_tc_kernel<128,3>", gemm_tc_kernel<128, false, false, 3>, TC_THREADS, 3 * 32768 + 1280);
+  dbg_occ("gemm_tc_persist_kernel", gemm_tc_persist_kernel<false>, PG_THREADS, PG_STAGES * 49152 + 1280);
+  dbg_occ("gemm_ln_kernel<3>", gemm_ln_kernel<3>, LN_THREADS, 3 * 32768 + 1024 + 256 + 2048 + 1536);
+  dbg_occ("gemm_ln_kernel<3> 192thr", gemm_ln_kernel<3>, 192, 3 * 32768 + 1024 + 256 + 2048 + 1536);
+  dbg_occ("gemm_ln_kernel<3> 64KB", gemm_ln_kernel<3>, LN_THREADS, 65536);
+  return 0;
+}

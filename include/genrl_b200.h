@@ -21,6 +21,7 @@ extern "C" {
 const char* genrl_last_error();
 int genrl_abi_version();
 int genrl_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* smem_optin);
+int genrl_debug_occupancy();   /* prints kernel attributes / occupancy to stderr (debug aid) */
 
 /* C[M,N] (+)= op(A) op(W)^T + bias.  Replaces nn.Linear / lowered nn.Conv2d / nn.ConvTranspose2d forward, dgrad and
  * wgrad (dreamer_utils.py:339-346, :733-735, :760, :586, :668).  in_dtype 1 -> tcgen05 + TMA kernel, 0 -> fp32 SIMT. */
