@@ -1166,8 +1166,39 @@ class _GruScan(Function):
         return dgx, dw, dg, db, None, dh0, None, None, None
 
 
+_SM_COUNT = None
+
+
+def scan_supported(D):
+    """the persistent scan keeps 8 hidden units (24 rows of W_h) per CTA resident in shared memory: D/8 CTAs must be co-resident"""
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        sm, ma, mi, opt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+        lib.load().genrl_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(opt))
+        _SM_COUNT = max(int(sm.value), 1)
+    return D % 8 == 0 and D // 8 <= _SM_COUNT
+
+
+def _gru_scan_stepwise(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
+    """Op-level recurrence for hidden sizes the resident-weight scan cannot hold (D > 8 x #SMs, e.g. BASELINE configs[4] with D = 4096):
+    per step one W_h GEMM (weights streamed from L2/HBM) + the GRU gate kernel, sequenced by autograd."""
+    D = gx.shape[1] // 3
+    gx3 = gx.reshape(B, T, 3 * D)
+    m = None if mask is None else mask.reshape(B, T, 1).float()
+    h = torch.zeros(B, D, device=gx.device, dtype=torch.float32) if h0 is None else h0.float()
+    outs = []
+    for t in range(T):
+        hp = h if m is None else h * m[:, t]
+        z = gx3[:, t].float() + linear(to_compute(hp), w_gru, None, out_fp32=True, wcols=(Hd, Hd + D))
+        h = gru_gates(z, gamma, beta, hp)
+        outs.append(h)
+    return torch.stack(outs, 1).reshape(B * T, D)
+
+
 def gru_scan(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
     """gx fp32 [B*T, 3D] (x-part pre-activations incl. nothing else), returns deter fp32 [B*T, D] (row n = b*T + t)."""
+    if not scan_supported(gx.shape[1] // 3):
+        return _gru_scan_stepwise(gx, w_gru, gamma, beta, mask, h0, B, T, Hd)
     return _GruScan.apply(gx, w_gru, gamma, beta, mask, h0, B, T, Hd)
 
 

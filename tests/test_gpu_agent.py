@@ -231,3 +231,30 @@ def test_ragged_shapes_resets_and_graph_replay_bf16():
     for a, b in zip(losses[False], losses[True]):
         for x, y in zip(a, b):
             assert abs(x - y) <= 2e-2 * max(1.0, abs(x)), (losses[False], losses[True])
+
+
+def test_large_rssm_config_runs_on_the_op_level_path():
+    """BASELINE configs[4] shape: deter = hidden = 4096, stoch 48x48 (K = 48 takes the generic categorical kernels, D = 4096 the
+    op-level recurrence because the resident-weight scan holds at most 8 x #SMs hidden units); small batch, bf16."""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from genrl_b200.synthetic import synthetic_batch
+    B, T, A, H = 2, 16, 10, 3
+    big = dict(ensemble=1, hidden=4096, deter=4096, stoch=48, discrete=48, norm="layer", std_act="softplus", min_std=0.1)
+    cfg = genrl_config(device=DEV, precision=16, batch_size=B, batch_length=T, imag_horizon=H,
+                       rssm=dict(big, single_obs_posterior=True), connector_rssm=dict(big, single_obs_posterior=False, learn_initial=True))
+    obs_space, act_spec = make_specs(action_dim=A, clip_dim=512)
+    torch.manual_seed(1)
+    agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    assert not ops.scan_supported(4096) and ops.scan_supported(1024)
+    ops.set_noise(ops.PhiloxNoise(3))
+    first = None
+    for i in range(3):
+        data = {k: v.to(DEV) for k, v in synthetic_batch(B, T, A, clip_dim=512, seed=5).items()}
+        state, outputs, metrics = agent.update_wm(data, i)
+        start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+        vals = {k: float(torch.as_tensor(metrics[k]).float().cpu().reshape(-1)[0]) for k in ("model_loss", "connector_model_loss", "actor_loss", "critic_loss")}
+        assert all(np.isfinite(v) for v in vals.values()), vals
+        assert outputs["post"]["stoch"].shape == (B, T, 48, 48) and state["deter"].shape == (B, 4096)
+        first = first or vals
+    assert vals["model_loss"] < first["model_loss"]          # three updates on the same batch reduce the world-model loss

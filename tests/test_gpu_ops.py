@@ -416,7 +416,7 @@ def test_adam_step_matches_oracle():
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("B,T,D,Hd,resets", [(3, 5, 64, 64, True), (50, 8, 256, 128, True), (7, 6, 1024, 1024, False), (70, 3, 128, 64, True)])
+@pytest.mark.parametrize("B,T,D,Hd,resets", [(3, 5, 64, 64, True), (50, 8, 256, 128, True), (7, 6, 1024, 1024, False), (70, 3, 128, 64, True), (4, 3, 1536, 256, True)])
 def test_gru_scan_matches_stepwise(dtype, B, T, D, Hd, resets):
     """persistent scan kernel == T sequential GRU steps (forward values, dgx, dW_h, dgamma, dh0)"""
     with ops.use_dtype(dtype):
