@@ -268,8 +268,12 @@ def run_native(args):
                     "d2h_bytes_per_step": d2h_bytes, "pipeline": "pinned host batch i+1 copied on a second stream while step i runs; loss of every step read back"},
             "gpu_launches": int(launches), "clocks": clk}
 
-    if rank == 0 and not args.no_roofline:
+    if rank == 0 and world == 1 and not args.no_roofline:
         line["roofline"], line["kernel_breakdown"] = roofline_pass(step, devb, nb, lib, args, agent)
+    elif rank == 0 and world > 1:
+        # the roofline pass re-runs eager steps on ONE rank; with data parallelism attached those steps contain NCCL collectives
+        # the other ranks would never join (it hung an 8-GPU run), and the kernel metric is a single-GPU quantity anyway
+        line["roofline_note"] = "single-GPU kernel metric: reported by the N=1 run only"
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, agent)
     if rank == 0:

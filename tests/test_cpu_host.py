@@ -136,3 +136,15 @@ def test_product_never_imports_the_oracle():
     bench = open(os.path.join(ROOT, "bench.py")).read()
     native = bench[bench.index("def run_native"):bench.index("def roofline_pass")]
     assert "oracle" not in native.replace("cpu_baseline", "")
+
+
+def test_bench_roofline_pass_is_single_gpu_only():
+    """the roofline pass re-runs eager steps on rank 0 only; under data parallelism those steps contain NCCL collectives the other
+    ranks never join (it deadlocked an 8-GPU run) — it must be gated on world == 1, like the CPU baseline"""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    call = src.index("roofline_pass(step, devb, nb, lib, args, agent)")
+    guard = src.rfind("\n    if ", 0, call)
+    assert "world == 1" in src[guard:call], src[guard:call]
+    cb = src.index('line["cpu_baseline"] = cpu_baseline(args, agent)')
+    guard = src.rfind("\n    if ", 0, cb)
+    assert "world == 1" in src[guard:cb]
