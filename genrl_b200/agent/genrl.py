@@ -55,6 +55,34 @@ class GenRLAgent(DreamerAgent):
     def update_wm(self, data, step):
         return super().update_wm(data, step)
 
+    def report(self, data, key="observation", nvid=8):
+        """reference genrl.py:64-106 with viclip_encode: true — the open-loop Dreamer video plus `video_clip_pred`: the first n_frames are
+        reconstructed from the posterior, the rest is imagined by the connector from the clip's video embeddings (held for n_frames each)
+        starting at the last posterior state, decoded, and stacked [truth | model | error] along the image height.
+        Inference-only composition of the kernels the update uses (encoder, observe, connector rollout, decoder)."""
+        report_data = super().report(data)
+        if not getattr(self.cfg, "viclip_encode", False):
+            raise NotImplementedError("online InternVideo2 encoding is out of scope; report needs data['clip_video'] (viclip_encode: true)")
+        wm = self.wm
+        nf = wm.connector.n_frames
+        with torch.no_grad(), self._ctx():
+            self.ensure_store()
+            decoder = wm.heads["decoder"]
+            truth = data[key][:nvid].float() / 255.0
+            B, T = truth.shape[0], truth.shape[1] - nf                      # frames after the n_frames warm-up
+            embed = wm.encoder(data)
+            states, _ = wm.rssm.observe(embed[:nvid, :nf], data["action"][:nvid, :nf], data["is_first"][:nvid, :nf])
+            recon = decoder(wm.decoder_input_fn(states))[key].mean[:nvid]
+            last = {k: v[:, -1] for k, v in states.items()}
+            # one embedding per n_frames chunk (the chunk's last frame), repeated over the chunk: these are the connector's "actions"
+            clip = data["clip_video"][:nvid, 2 * nf - 1::nf].to(self.device)
+            clip = clip.reshape(B, T // nf, 1, -1).expand(B, T // nf, nf, clip.shape[-1]).reshape(B, T, -1)
+            prior = wm.connector.video_imagine(clip, last, reset_every_n_frames=False)
+            imagined = decoder(wm.decoder_input_fn(prior))[key].mean
+            model = torch.clip(torch.cat([recon[:, :nf] + 0.5, imagined + 0.5], 1), 0, 1)
+            report_data["video_clip_pred"] = torch.cat([truth, model, (model - truth + 1) / 2], 3)
+        return report_data
+
     def update_imag_behavior(self, state=None, outputs=None, metrics={}, seq_data=None):
         """reference genrl.py:108-124"""
         if getattr(self.cfg, "imag_reward_fn", None) is None:
