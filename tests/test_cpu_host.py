@@ -148,3 +148,32 @@ def test_bench_roofline_pass_is_single_gpu_only():
     cb = src.index('line["cpu_baseline"] = cpu_baseline(args, agent)')
     guard = src.rfind("\n    if ", 0, cb)
     assert "world == 1" in src[guard:cb]
+
+
+def test_header_and_sources_declare_the_same_entry_points():
+    """every extern "C" genrl_* function defined in csrc/ is declared in include/genrl_b200.h and vice versa (argument counts match)"""
+    import re
+    csrc = os.path.join(ROOT, "genrl_b200", "csrc")
+    defined = {}
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith(".cu"):
+            text = open(os.path.join(csrc, f)).read()
+            for m in re.finditer(r'extern "C"\s+(?:const char\*|int|long long)\s+(genrl_\w+)\s*\(([^)]*)\)\s*\{', text, re.S):
+                args = m.group(2).strip()
+                defined[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    protos = parse_header()
+    assert set(defined) == set(protos), set(defined) ^ set(protos)
+    for name, (_, argtypes, _) in protos.items():
+        assert len(argtypes) == defined[name], (name, len(argtypes), defined[name])
+
+
+def test_graph_call_structure_helpers_roundtrip():
+    from genrl_b200.graphs import _flatten, _rebuild
+    a, b, c = torch.zeros(2), torch.ones(3), torch.arange(4)
+    obj = ({"x": a, "y": {"z": b}}, [c, 5, "s"], 7)
+    flat = _flatten(obj, [])
+    assert [p for p, _ in flat] == ["/0/x", "/0/y/z", "/1/0"]
+    new = [t + 1 for _, t in flat]
+    out = _rebuild(obj, iter(new))
+    assert torch.equal(out[0]["x"], a + 1) and torch.equal(out[0]["y"]["z"], b + 1) and torch.equal(out[1][0], c + 1)
+    assert out[1][1:] == [5, "s"] and out[2] == 7
