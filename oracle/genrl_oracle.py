@@ -576,6 +576,57 @@ def behavior_losses(P, beh_pre, start, cfg, tape, ema_vals, reward_fn=None, acto
 
 
 # --------------------------------------------------------------------------------------
+# VLM reward of the imagination behaviour (tools/genrl_utils.py:240-370, agent/genrl.yaml:21; agent/video_utils.py:209-239)
+# --------------------------------------------------------------------------------------
+def connector_video_imagine(P, video_embed, cfg, tape, sample=True, denoise=False, pre="wm.connector", n_frames=8):
+    """VideoSSM.video_imagine with dreamer_init=None and reset_every_n_frames=False (video_utils.py:209-239): optional denoising of
+    the embeddings by the aligner, learned initial state from the first action, open-loop prior rollout over the embedding actions."""
+    r = cfg["connector_rssm"]
+    S, K = r["stoch"], r["discrete"]
+    if denoise and cfg["connector"]["denoising_ae"]:
+        video_embed = F.normalize(aligner(P, f"{pre}.aligner", video_embed), dim=-1)
+    action = connector_get_action(video_embed, n_frames, cfg["connector"]["rescale_embeds"])
+    init = connector_initial(P, pre, action[:, 0], tape, S, K)
+    return imagine_prior(P, pre, action, init, tape, S, K, sample)
+
+
+def unconditional_target(P, prompt_embed, n_rows, steps, cfg, tape, skip_first=True, sample=False):
+    """The cached target of video_text_reward (genrl_utils.py:305-316): the connector's rollout from the prompt embedding repeated over
+    time, denoised, first step dropped when skip_first_target, returned time-major [steps, n_rows, ...]."""
+    ve = prompt_embed.reshape(1, 1, -1).repeat(n_rows, steps + (1 if skip_first else 0), 1)
+    stats = connector_video_imagine(P, ve, cfg, tape, sample=sample, denoise=True)
+    if skip_first:
+        stats = {k: v[:, 1:] for k, v in stats.items()}
+    return {k: v.transpose(0, 1).contiguous() for k, v in stats.items()}
+
+
+def max_cosine(u, v):
+    """genrl_utils.py:240-242: dot product of the two vectors after dividing both by the larger of their norms."""
+    m = torch.maximum(u.norm(dim=-1), v.norm(dim=-1)).unsqueeze(-1)
+    return ((u / m) * (v / m)).sum(-1)
+
+
+def vlm_reward(P, seq, target, n_frames=8, align_sequence=True):
+    """video_text_reward with score_fn='max_cosine' on the decoder's input projection of the flattened stoch (compute_reward,
+    genrl_utils.py:250-258).  align_sequence (:344-366): score every n_frames window of the agent sequence against the first n_frames of
+    the target, take the best window start t* per row, and compare the agent sequence with the target shifted to start at t*
+    (target index clip(cumsum(cumsum(one_hot(t*))) - 1, 0), i.e. 0 before t* and counting up from it)."""
+    W, b = P["wm.heads.decoder._conv_in.0.weight"], P["wm.heads.decoder._conv_in.0.bias"]
+    proj = lambda st: F.linear(st.reshape(tuple(st.shape[:-2]) + (-1,)), W, b)
+    score = lambda agent_stoch, target_stoch: max_cosine(proj(target_stoch), proj(agent_stoch))
+    if not align_sequence:
+        return score(seq["stoch"], target["stoch"]).unsqueeze(-1)
+    T = seq["deter"].shape[0]
+    head = target["stoch"][:n_frames]
+    window_scores = torch.stack([score(seq["stoch"][t:t + n_frames], head).mean(0) for t in range(T - n_frames)], 0)     # [T-nf, N]
+    best = F.one_hot(window_scores.argmax(0), num_classes=target["stoch"].shape[0])                                     # [N, T_target]
+    idx = torch.clip(torch.cumsum(torch.cumsum(best, 1), 1) - 1, min=0).T                                                # [T_target, N]
+    ts = target["stoch"]
+    shifted = torch.gather(ts, 0, idx.reshape(idx.shape + (1, 1)).expand(idx.shape + tuple(ts.shape[2:])))
+    return score(seq["stoch"], shifted).unsqueeze(-1)
+
+
+# --------------------------------------------------------------------------------------
 # optimizer (Optimizer.__call__ dreamer_utils.py:892-932 around torch.optim.Adam)
 # --------------------------------------------------------------------------------------
 class AdamState:
@@ -735,6 +786,13 @@ class OracleAgent:
         self.last_actor_grads, self.last_critic_grads = agr, cgr
         self.last_seq, self.last_target = seq, target.detach()
         return {f"{prefix}{k}": v for k, v in out.items()}
+
+    def update_imag_behavior(self, outs, target, n_frames=8):
+        """GenRLAgent.update_imag_behavior (genrl.py:108-124) with imag_reward_fn = video_text_reward and the cached `target`."""
+        args = self.cfg["imag_reward_args"]
+        assert args["score_fn"] == "max_cosine" and not args["align_initial"] and not args["weighted_align"]
+        fn = lambda seq: vlm_reward(self.P, seq, target, n_frames, bool(args["align_sequence"]))
+        return self.update_behavior(outs, beh="_imag_behavior", reward_fn=fn, prefix="imag_")
 
     def update(self, data):
         """DreamerAgent.update (dreamer.py:94-97)."""

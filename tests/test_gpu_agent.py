@@ -258,3 +258,49 @@ def test_large_rssm_config_runs_on_the_op_level_path():
         assert outputs["post"]["stoch"].shape == (B, T, 48, 48) and state["deter"].shape == (B, 4096)
         first = first or vals
     assert vals["model_loss"] < first["model_loss"]          # three updates on the same batch reduce the world-model loss
+
+
+import os as _os
+
+
+@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
+                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
+def test_agent_vlm_reward_imag_behavior_matches_reference_golden_fp32():
+    """SURVEY §8 a19/a20 on the CUDA path: cached connector target, video_text_reward and update_imag_behavior vs the reference's golden
+    vectors (tests/golden/tiny_genrl_vlm.*, pinned on CPU by tests/test_oracle_golden.py)."""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from tests.test_oracle_golden import _load_vlm_case
+    g, meta, _ = _load_vlm_case()
+    cfg = genrl_config(device=DEV, precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    torch.manual_seed(1)
+    agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    agent.load_state_dict(g["init"], strict=True)
+    data = {k: v.to(DEV) for k, v in g["data"].items()}
+    args = cfg.imag_reward_args
+    N, steps = meta["B"] * meta["T"], meta["H"] + 1
+    # the cached target, created the way genrl_utils.video_text_reward would (skip_first_target), on the reference's draws
+    ops.set_noise(ops.TapeNoise(g["target_tape"], DEV))
+    with torch.no_grad(), agent._ctx():
+        agent.ensure_store()
+        ve = g["prompt"].to(DEV).reshape(1, 1, -1).repeat(N, steps + 1, 1)
+        stats = agent.wm.connector.video_imagine(ve, dreamer_init=None, sample=args["sample_for_target"], reset_every_n_frames=False, denoise=True)
+        agent.unconditional_target = {k: v[:, 1:].permute([1, 0] + list(range(2, v.dim()))).contiguous() for k, v in stats.items()}
+    assert torch.equal(agent.unconditional_target["stoch"].float().cpu(), g["target"]["stoch"])
+    relclose(agent.unconditional_target["logit"], g["target"]["logit"], 1e-4, 2e-5, "target logit")
+    ops.set_noise(ops.TapeNoise(g["tape"], DEV))
+    for step in range(2):
+        state, outputs, metrics = agent.update_wm(data, step)
+        start, metrics = agent.update_imag_behavior(state, outputs, metrics, seq_data=data)
+        for k, v in meta["metrics"][step].items():
+            assert k in metrics, f"metric {k} missing"
+            mv = float(torch.as_tensor(metrics[k]).float().cpu().reshape(-1)[0])
+            tol = 2e-3 if k.endswith("grad_norm") else 2e-4
+            assert abs(mv - v) <= tol * max(1.0, abs(v)) + 1e-5, f"step {step} metric {k}: {mv} vs reference {v}"
+    sd = agent.state_dict()
+    for k, v in g["params"].items():
+        err = float((sd[k].float().cpu() - v).abs().max())
+        assert err <= 5e-6 + 1e-4 * float(v.abs().max()), f"parameter {k} after 2 updates: err {err:.3e}"
+    ops.set_noise(ops.PhiloxNoise(0))

@@ -54,3 +54,62 @@ def test_multinomial_identity():
     torch.manual_seed(5)
     q = torch.empty_like(p).exponential_(1)
     assert torch.equal(a, torch.argmax(p / q, -1))
+
+
+def _load_vlm_case():
+    import json, os
+    from tests.golden_utils import GOLDEN
+    from genrl_b200.config import genrl_config
+    z = np.load(os.path.join(GOLDEN, "tiny_genrl_vlm.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "tiny_genrl_vlm.json")))
+    g = {"init": {}, "data": {}, "target": {}, "reward": {}, "params": {}, "tape": [], "target_tape": []}
+    for k in z.files:
+        arr = torch.from_numpy(z[k])
+        if k == "prompt_embedding":
+            g["prompt"] = arr
+            continue
+        head, rest = k.split("/", 1)
+        if head in ("tape", "target_tape"):
+            g[head].append((rest, arr))
+        elif head == "ref1":
+            g["params"][rest[len("params/"):]] = arr
+        elif head == "reward":
+            g["reward"][int(rest)] = arr
+        else:
+            g[head][rest] = arr
+    for t in ("tape", "target_tape"):
+        g[t] = [(name.split("_", 1)[1], v) for name, v in sorted(g[t], key=lambda kv: kv[0])]
+    cfg = genrl_config(device="cpu", precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    return g, meta, cfg
+
+
+def test_oracle_vlm_reward_imag_behavior_matches_reference_golden(monkeypatch):
+    """video_text_reward (max_cosine on the decoder projection, sliding-window sequence alignment against the cached
+    connector target) + update_imag_behavior of the UNMODIFIED reference, reproduced by the oracle: target, rewards, metrics, parameters."""
+    torch.set_num_threads(1)
+    g, meta, cfg = _load_vlm_case()
+    agent = O.OracleAgent(g["init"], cfg, kind="genrl")
+    args = cfg["imag_reward_args"]
+    N, steps = meta["B"] * meta["T"], meta["H"] + 1
+    target = O.unconditional_target(agent.P, g["prompt"], N, steps, cfg, O.NoiseTape(replay=g["target_tape"]),
+                                    skip_first=args["skip_first_target"], sample=args["sample_for_target"])
+    assert torch.equal(target["stoch"], g["target"]["stoch"])                 # one-hot target latents bit-exact
+    for k in ("deter", "logit"):
+        torch.testing.assert_close(target[k], g["target"][k], rtol=2e-5, atol=2e-6)
+    rewards = []
+    real = O.vlm_reward
+    monkeypatch.setattr(O, "vlm_reward", lambda *a, **k: rewards.append(real(*a, **k)) or rewards[-1])
+    agent.tape = O.NoiseTape(replay=g["tape"])
+    for step in range(2):
+        state, outs, mets = agent.update_wm(g["data"])
+        mets.update(agent.update_imag_behavior(outs, target))
+        torch.testing.assert_close(rewards[step].detach(), g["reward"][step], rtol=2e-5, atol=2e-6)
+        assert rewards[step].shape == (steps, N, 1)
+        for k, v in meta["metrics"][step].items():
+            assert k in mets, k
+            np.testing.assert_allclose(float(mets[k]), v, rtol=1e-4, atol=1e-6, err_msg=k)
+    assert agent.tape.pos == len(agent.tape.items)
+    assert any(k.startswith("imag_") for k in meta["metrics"][0])
+    for k, v in g["params"].items():
+        torch.testing.assert_close(agent.P[k], v, rtol=1e-5, atol=2e-6, msg=lambda m: f"{k}: {m}")
