@@ -578,15 +578,18 @@ def behavior_losses(P, beh_pre, start, cfg, tape, ema_vals, reward_fn=None, acto
 # --------------------------------------------------------------------------------------
 # VLM reward of the imagination behaviour (tools/genrl_utils.py:240-370, agent/genrl.yaml:21; agent/video_utils.py:209-239)
 # --------------------------------------------------------------------------------------
-def connector_video_imagine(P, video_embed, cfg, tape, sample=True, denoise=False, pre="wm.connector", n_frames=8):
-    """VideoSSM.video_imagine with dreamer_init=None and reset_every_n_frames=False (video_utils.py:209-239): optional denoising of
-    the embeddings by the aligner, learned initial state from the first action, open-loop prior rollout over the embedding actions."""
+def connector_video_imagine(P, video_embed, cfg, tape, sample=True, denoise=False, dreamer_init=None, pre="wm.connector", n_frames=8):
+    """VideoSSM.video_imagine with reset_every_n_frames=False (video_utils.py:209-239): optional denoising of the embeddings by the
+    aligner, learned initial state from the first action (its stoch replaced by dreamer_init's when given: cell_input == 'stoch'),
+    open-loop prior rollout over the embedding actions."""
     r = cfg["connector_rssm"]
     S, K = r["stoch"], r["discrete"]
     if denoise and cfg["connector"]["denoising_ae"]:
         video_embed = F.normalize(aligner(P, f"{pre}.aligner", video_embed), dim=-1)
     action = connector_get_action(video_embed, n_frames, cfg["connector"]["rescale_embeds"])
     init = connector_initial(P, pre, action[:, 0], tape, S, K)
+    if dreamer_init is not None:
+        init["stoch"] = dreamer_init["stoch"]
     return imagine_prior(P, pre, action, init, tape, S, K, sample)
 
 
@@ -624,6 +627,50 @@ def vlm_reward(P, seq, target, n_frames=8, align_sequence=True):
     ts = target["stoch"]
     shifted = torch.gather(ts, 0, idx.reshape(idx.shape + (1, 1)).expand(idx.shape + tuple(ts.shape[2:])))
     return score(seq["stoch"], shifted).unsqueeze(-1)
+
+
+# --------------------------------------------------------------------------------------
+# report(): open-loop video prediction (dreamer.py:98-108, :307-321) and text/video-conditioned prediction (genrl.py:64-106)
+# --------------------------------------------------------------------------------------
+def video_pred(P, data, cfg, tape, nvid=8, ctx=5):
+    """WorldModel.video_pred: reconstruct the first `ctx` frames from the posterior, imagine the rest open loop from the recorded actions,
+    return [truth | model | error] stacked along the image height, [nvid, T, 3, 3*64, 64]."""
+    r = cfg["rssm"]
+    S, K, D = r["stoch"], r["discrete"], r["deter"]
+    obs = preprocess_obs(data["observation"])
+    truth = obs[:nvid] + 0.5
+    embed = encoder(P, "wm.encoder", obs)
+    states, _ = observe(P, "wm.rssm", embed[:nvid, :ctx], data["action"][:nvid, :ctx], data["is_first"][:nvid, :ctx], tape, S, K, D,
+                        single_obs_posterior=r["single_obs_posterior"])
+    dec_in = lambda st: st["stoch"].reshape(tuple(st["stoch"].shape[:-2]) + (-1,))          # decoder_inputs: stoch (dreamer.py:138-140)
+    recon = decoder(P, "wm.heads.decoder", dec_in(states))
+    init = {k: v[:, -1] for k, v in states.items()}
+    prior = imagine_prior(P, "wm.rssm", data["action"][:nvid, ctx:], init, tape, S, K)
+    prior_recon = decoder(P, "wm.heads.decoder", dec_in(prior))
+    model = torch.clip(torch.cat([recon[:, :ctx] + 0.5, prior_recon + 0.5], 1), 0, 1)
+    return torch.cat([truth, model, (model - truth + 1) / 2], 3)
+
+
+def video_clip_pred(P, data, cfg, tape, nvid=8, n_frames=8):
+    """GenRLAgent.report (viclip_encode: true): posterior reconstruction of the first n_frames, then the connector's rollout from the
+    batch's video embeddings (one per n_frames chunk, held over the chunk) starting at the last posterior stoch, decoded."""
+    r = cfg["rssm"]
+    S, K, D = r["stoch"], r["discrete"], r["deter"]
+    obs = preprocess_obs(data["observation"])
+    truth = obs[:nvid] + 0.5
+    B, T = truth.shape[0], truth.shape[1] - n_frames
+    embed = encoder(P, "wm.encoder", obs)
+    states, _ = observe(P, "wm.rssm", embed[:nvid, :n_frames], data["action"][:nvid, :n_frames], data["is_first"][:nvid, :n_frames], tape,
+                        S, K, D, single_obs_posterior=r["single_obs_posterior"])
+    dec_in = lambda st: st["stoch"].reshape(tuple(st["stoch"].shape[:-2]) + (-1,))
+    recon = decoder(P, "wm.heads.decoder", dec_in(states))
+    last = {k: v[:, -1] for k, v in states.items()}
+    ve = data["clip_video"][:nvid, 2 * n_frames - 1::n_frames]
+    ve = ve.reshape(B, T // n_frames, 1, -1).repeat(1, 1, n_frames, 1).reshape(B, T, -1)
+    prior = connector_video_imagine(P, ve, cfg, tape, sample=True, denoise=False, dreamer_init=last)
+    prior_recon = decoder(P, "wm.heads.decoder", dec_in(prior))
+    model = torch.clip(torch.cat([recon[:, :n_frames] + 0.5, prior_recon + 0.5], 1), 0, 1)
+    return torch.cat([truth, model, (model - truth + 1) / 2], 3)
 
 
 # --------------------------------------------------------------------------------------

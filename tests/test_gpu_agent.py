@@ -304,3 +304,30 @@ def test_agent_vlm_reward_imag_behavior_matches_reference_golden_fp32():
         err = float((sd[k].float().cpu() - v).abs().max())
         assert err <= 5e-6 + 1e-4 * float(v.abs().max()), f"parameter {k} after 2 updates: err {err:.3e}"
     ops.set_noise(ops.PhiloxNoise(0))
+
+
+@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
+                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
+def test_agent_report_videos_match_reference_golden_fp32():
+    """SURVEY §8 f3 on the CUDA path: DreamerAgent.report / GenRLAgent.report vs the reference's golden videos
+    (tests/golden/tiny_genrl_report.*, pinned on CPU by tests/test_oracle_golden.py)."""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from tests.test_oracle_golden import _load_report_case
+    g, meta, _ = _load_report_case()
+    cfg = genrl_config(device=DEV, precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    torch.manual_seed(1)
+    agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    agent.load_state_dict(g["init"], strict=True)
+    data = {k: v.to(DEV) for k, v in g["data"].items()}
+    ops.set_noise(ops.TapeNoise(g["tape"], DEV))
+    rep = agent.report(data)
+    assert ops.noise.pos == len(ops.noise.items), "every reference draw must be consumed"
+    assert set(rep) == {"openl_observation", "video_clip_pred"}
+    for k, ref in g["report"].items():
+        v = rep[k].float().cpu()
+        assert v.shape == (meta["B"], meta["T"], 3, 192, 64)
+        relclose(v[:, :, :, 64:128], ref.float(), 0.0, 2e-3, f"{k} model frames")
+    ops.set_noise(ops.PhiloxNoise(0))

@@ -113,3 +113,44 @@ def test_oracle_vlm_reward_imag_behavior_matches_reference_golden(monkeypatch):
     assert any(k.startswith("imag_") for k in meta["metrics"][0])
     for k, v in g["params"].items():
         torch.testing.assert_close(agent.P[k], v, rtol=1e-5, atol=2e-6, msg=lambda m: f"{k}: {m}")
+
+
+def _load_report_case():
+    import json, os
+    from tests.golden_utils import GOLDEN
+    from genrl_b200.config import genrl_config
+    z = np.load(os.path.join(GOLDEN, "tiny_genrl_report.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "tiny_genrl_report.json")))
+    shared = np.load(os.path.join(GOLDEN, meta["init_from"]))
+    g = {"init": {k[len("init/"):]: torch.from_numpy(shared[k]) for k in shared.files if k.startswith("init/")}, "data": {}, "report": {}, "tape": []}
+    for k in z.files:
+        head, rest = k.split("/", 1)
+        arr = torch.from_numpy(z[k])
+        if head == "tape":
+            g["tape"].append((rest, arr))
+        else:
+            g[head][rest] = arr
+    g["tape"] = [(name.split("_", 1)[1], v) for name, v in sorted(g["tape"], key=lambda kv: kv[0])]
+    cfg = genrl_config(device="cpu", precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    return g, meta, cfg
+
+
+def test_oracle_report_videos_match_reference_golden():
+    """agent.report() of the UNMODIFIED reference — `openl_observation` (WorldModel.video_pred, dreamer.py:307-321) and
+    `video_clip_pred` (GenRLAgent.report, genrl.py:64-106) — reproduced by the oracle on the reference's recorded draws."""
+    torch.set_num_threads(1)
+    g, meta, cfg = _load_report_case()
+    agent = O.OracleAgent(g["init"], cfg, kind="genrl")
+    agent.tape = O.NoiseTape(replay=g["tape"])
+    data = agent.cast(g["data"])
+    with torch.no_grad():
+        vids = {"openl_observation": O.video_pred(agent.P, data, cfg, agent.tape), "video_clip_pred": O.video_clip_pred(agent.P, data, cfg, agent.tape)}
+    assert agent.tape.pos == len(agent.tape.items)
+    for k, v in vids.items():
+        assert v.shape == (meta["B"], meta["T"], 3, 192, 64)
+        model = v[:, :, :, 64:128]
+        torch.testing.assert_close(model, g["report"][k].float(), rtol=0, atol=1e-3)          # the fixture stores the model third in fp16
+        truth = g["data"]["observation"].float() / 255.0
+        torch.testing.assert_close(v[:, :, :, :64], truth, rtol=0, atol=1e-6)
+        torch.testing.assert_close(v[:, :, :, 128:], (model - truth + 1) / 2, rtol=0, atol=1e-6)
