@@ -674,6 +674,29 @@ def video_clip_pred(P, data, cfg, tape, nvid=8, n_frames=8):
 
 
 # --------------------------------------------------------------------------------------
+# acting (DreamerAgent.act, dreamer.py:41-64): one encoder + obs_step + actor evaluation per environment step, batch 1
+# --------------------------------------------------------------------------------------
+def act_step(P, obs, state, cfg, tape, eval_mode, act_dim):
+    """obs: dict of un-batched numpy/torch values (observation uint8 [3,64,64], is_first bool, ...); state: None or (latent, action).
+    Returns (action [act_dim], new_state).  The latent is always sampled (eval_state_mean: False); the action is the policy mean in eval
+    mode and a reparameterised sample otherwise."""
+    r = cfg["rssm"]
+    S, K, D = r["stoch"], r["discrete"], r["deter"]
+    ob = preprocess_obs(torch.as_tensor(obs["observation"]).unsqueeze(0))
+    is_first = torch.as_tensor(obs["is_first"]).reshape(1)
+    if state is None:
+        latent, action = rssm_initial(1, S, K, D, ob.dtype), torch.zeros(1, act_dim, dtype=ob.dtype)
+    else:
+        latent, action = state
+    embed = encoder(P, "wm.encoder", ob)
+    should_sample = (not eval_mode) or (not cfg["eval_state_mean"])
+    latent, _ = obs_step(P, "wm.rssm", latent, action, embed, is_first, tape, S, K, r["single_obs_posterior"], should_sample)
+    mean, std = actor_dist(P, "_acting_behavior.actor", get_feat(latent), cfg["actor"]["layers"])
+    action = mean if eval_mode else mean + std * tape.randn(mean)
+    return action[0], (latent, action)
+
+
+# --------------------------------------------------------------------------------------
 # optimizer (Optimizer.__call__ dreamer_utils.py:892-932 around torch.optim.Adam)
 # --------------------------------------------------------------------------------------
 class AdamState:

@@ -331,3 +331,26 @@ def test_agent_report_videos_match_reference_golden_fp32():
         assert v.shape == (meta["B"], meta["T"], 3, 192, 64)
         relclose(v[:, :, :, 64:128], ref.float(), 0.0, 2e-3, f"{k} model frames")
     ops.set_noise(ops.PhiloxNoise(0))
+
+
+@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
+                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
+def test_agent_act_matches_reference_golden_fp32():
+    """SURVEY §8 f4 on the CUDA path: agent.act() over the reference's 6-step episode (tests/golden/tiny_genrl_act.*)."""
+    from genrl_b200 import ops
+    from genrl_b200.agent.genrl import GenRLAgent
+    from tests.test_oracle_golden import _load_act_case, act_observation
+    g, meta, _ = _load_act_case()
+    cfg = genrl_config(device=DEV, precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    torch.manual_seed(1)
+    agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    agent.load_state_dict(g["init"], strict=True)
+    ops.set_noise(ops.TapeNoise(g["tape"], DEV))
+    state = None
+    for i, (first, ev) in enumerate(meta["steps"]):
+        a, state = agent.act(act_observation(g["observation"][i], first), None, i, eval_mode=ev, state=state)
+        assert np.abs(np.asarray(a) - g["actions"][i]).max() <= 1e-4, f"step {i}: {a} vs {g['actions'][i]}"
+    assert ops.noise.pos == len(ops.noise.items), "every reference draw must be consumed"
+    ops.set_noise(ops.PhiloxNoise(0))

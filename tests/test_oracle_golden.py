@@ -154,3 +154,38 @@ def test_oracle_report_videos_match_reference_golden():
         truth = g["data"]["observation"].float() / 255.0
         torch.testing.assert_close(v[:, :, :, :64], truth, rtol=0, atol=1e-6)
         torch.testing.assert_close(v[:, :, :, 128:], (model - truth + 1) / 2, rtol=0, atol=1e-6)
+
+
+def _load_act_case():
+    import json, os
+    from tests.golden_utils import GOLDEN
+    from genrl_b200.config import genrl_config
+    z = np.load(os.path.join(GOLDEN, "tiny_genrl_act.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "tiny_genrl_act.json")))
+    shared = np.load(os.path.join(GOLDEN, meta["init_from"]))
+    g = {"init": {k[len("init/"):]: torch.from_numpy(shared[k]) for k in shared.files if k.startswith("init/")},
+         "observation": z["observation"], "actions": z["actions"],
+         "tape": [(k.split("/", 1)[1].split("_", 1)[1], torch.from_numpy(z[k])) for k in sorted(f for f in z.files if f.startswith("tape/"))]}
+    cfg = genrl_config(device="cpu", precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    return g, meta, cfg
+
+
+def act_observation(obs_u8, is_first):
+    return dict(observation=obs_u8, reward=np.zeros((), np.float32), is_first=np.array(bool(is_first)), is_last=np.array(False),
+                is_terminal=np.array(False), discount=np.ones((), np.float32))
+
+
+def test_oracle_act_matches_reference_golden():
+    """DreamerAgent.act (dreamer.py:41-64) of the UNMODIFIED reference over a 6-step episode (sampled and mean actions, one
+    reset, carried state) reproduced by the oracle on the recorded draws."""
+    torch.set_num_threads(1)
+    g, meta, cfg = _load_act_case()
+    agent = O.OracleAgent(g["init"], cfg, kind="genrl")
+    agent.tape = O.NoiseTape(replay=g["tape"])
+    state = None
+    with torch.no_grad():
+        for i, (first, ev) in enumerate(meta["steps"]):
+            a, state = O.act_step(agent.P, act_observation(g["observation"][i], first), state, cfg, agent.tape, ev, meta["A"])
+            np.testing.assert_allclose(a.numpy(), g["actions"][i], rtol=0, atol=2e-6, err_msg=f"step {i}")
+    assert agent.tape.pos == len(agent.tape.items)
