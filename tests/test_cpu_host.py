@@ -177,3 +177,31 @@ def test_graph_call_structure_helpers_roundtrip():
     out = _rebuild(obj, iter(new))
     assert torch.equal(out[0]["x"], a + 1) and torch.equal(out[0]["y"]["z"], b + 1) and torch.equal(out[1][0], c + 1)
     assert out[1][1:] == [5, "s"] and out[2] == 7
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/agent"), reason="needs the reference checkout (build container only)")
+def test_full_size_state_dict_is_checkpoint_compatible_with_the_reference():
+    """at the benchmark configuration (stickman, A = 10, 512-d video embeddings) the mirror's state_dict has the
+    reference's keys, shapes and dtypes, the same seeded initial values, and loads the reference's state_dict strictly."""
+    from genrl_b200.agent.genrl import GenRLAgent
+    from oracle.ref_harness import make_reference_agent
+    cfg = genrl_config(device="cpu", precision=32, batch_size=2, batch_length=16, imag_horizon=3)
+    obs_space, act_spec = make_specs(action_dim=10, clip_dim=512)
+    ref = make_reference_agent(cfg, obs_space, act_spec, kind="genrl", seed=1)
+    ref_sd = ref.state_dict()
+    del ref
+    torch.manual_seed(1)
+    mine = GenRLAgent(name="genrl", cfg=genrl_config(device="cpu", precision=32, batch_size=2, batch_length=16, imag_horizon=3),
+                      obs_space=obs_space, act_spec=act_spec)
+    sd = mine.state_dict()
+    assert list(sd) == list(ref_sd), [k for k in set(sd) ^ set(ref_sd)][:10]
+    n = 0
+    for k, v in ref_sd.items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+        assert torch.equal(sd[k], v), f"{k}: seeded initial values differ"
+        n += v.numel()
+    assert n > 59_000_000                                     # WM 43.3 M (incl. connector) + actor / critic / target critic = 59.6 M
+    shuffled = {k: v + 1 for k, v in ref_sd.items() if v.is_floating_point()}
+    missing = mine.load_state_dict({**ref_sd, **shuffled}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert torch.equal(mine.state_dict()["wm.rssm._cell._layer.weight"], ref_sd["wm.rssm._cell._layer.weight"] + 1)
