@@ -32,6 +32,9 @@ CASES = {
     "tiny_dreamer": dict(B=2, T=6, H=4, A=4, clip=32, resets=0.0, kind="dreamer",
                                 over={**tiny_overrides(units=32, stoch=4, discrete=8),
                                       "actor_ent": 3e-4}),
+    # BASELINE configs[3] flavour: 9 actions and an extra low-dimensional `state` observation key that the GenRL encoder/decoder ignore
+    # (conf/env/dmc_pixels.yaml mlp_keys '$^'); single sequence (B = 1) as the ragged edge
+    "tiny_kitchen": dict(B=1, T=16, H=4, A=9, clip=32, resets=0.2, kind="genrl", over=tiny_overrides(), extra_obs={"state": 30}, slim=True),
 }
 
 
@@ -44,9 +47,14 @@ def run_reference(case, seed=7):
     cfg = genrl_config(device="cpu", precision=32, batch_size=c["B"], batch_length=c["T"],
                        imag_horizon=c["H"], agent=c["kind"], **c["over"])
     obs_space, act_spec = make_specs(action_dim=c["A"], clip_dim=c["clip"], with_clip=True)
+    from genrl_b200.config import Spec
+    for k, d in c.get("extra_obs", {}).items():
+        obs_space[k] = Spec((d,), "float32")
     agent = make_reference_agent(cfg, obs_space, act_spec, kind=c["kind"], seed=1)
     init = {k: v.detach().clone() for k, v in agent.state_dict().items()}
     data = O.synthetic_batch(c["B"], c["T"], c["A"], clip_dim=c["clip"], seed=3, resets=c["resets"])
+    for k, d in c.get("extra_obs", {}).items():
+        data[k] = torch.rand(c["B"], c["T"], d, generator=torch.Generator().manual_seed(4))
     name_of = {id(p): n for n, p in agent.named_parameters()}
     grads_log = []
     orig_clip = torch.nn.utils.clip_grad_norm_
@@ -104,7 +112,10 @@ def compare(name, a, b, rtol=2e-5, atol=1e-6):
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)          # deterministic reduction order for the fixtures
+    selected = sys.argv[1:] or list(CASES)            # python -m oracle.make_golden [case ...]: regenerate only the named fixtures
     for case, c in CASES.items():
+        if case not in selected:
+            continue
         cfg, init, data, ref, ref_grads = run_reference(case)
         oagent, orc, orc_grads = run_oracle(cfg, init, data, c["kind"])
         worst = 0.0
@@ -141,8 +152,10 @@ def main():
         assert not bad and idx_equal, "oracle does not reproduce the reference"
 
         out = {}
-        for k, v in init.items():
-            out[f"init/{k}"] = to_np(v)
+        slim = bool(c.get("slim"))       # slim fixtures: no initial / final parameters and gradients (the seeded init is re-created by the
+        if not slim:                     # mirror and checked by hash; losses and grad norms of BOTH updates still pin the optimizer steps)
+            for k, v in init.items():
+                out[f"init/{k}"] = to_np(v)
         for k, v in data.items():
             out[f"data/{k}"] = to_np(v)
         for i, (kind, v) in enumerate(oagent.tape.items):
@@ -156,13 +169,18 @@ def main():
                 out[f"ref{step}/outputs/{k}"] = to_np(r["outputs"][k])
             for k, v in r["outputs"]["likes"].items():
                 out[f"ref{step}/outputs/likes/{k}"] = to_np(v)
-            if step == 1:                       # parameters after both updates (keeps the fixture small)
+            if step == 1 and not slim:          # parameters after both updates (keeps the fixture small)
                 for k, v in r["params"].items():
                     out[f"ref{step}/params/{k}"] = to_np(v)
-        for i, rg in enumerate(ref_grads):
-            for k, v in rg.items():
-                out[f"grads/{i}/{k}"] = to_np(v)
-        meta = dict(case=case, **{k: v for k, v in c.items() if k != "over"}, overrides=c["over"],
+        if not slim:
+            for i, rg in enumerate(ref_grads):
+                for k, v in rg.items():
+                    out[f"grads/{i}/{k}"] = to_np(v)
+        import hashlib
+        sha = hashlib.sha256()
+        for k in sorted(init):
+            sha.update(k.encode()); sha.update(to_np(init[k]).tobytes())
+        meta = dict(case=case, **{k: v for k, v in c.items() if k != "over"}, overrides=c["over"], init_sha256=sha.hexdigest(),
                     torch=torch.__version__, threads=torch.get_num_threads(), seed_init=1, seed_data=3, seed_run=7,
                     metrics=[r["metrics"] for r in ref], reference_commit="4cd8394",
                     grad_order=(["wm", "connector", "actor", "critic"] if c["kind"] == "genrl"

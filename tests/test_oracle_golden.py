@@ -189,3 +189,45 @@ def test_oracle_act_matches_reference_golden():
             a, state = O.act_step(agent.P, act_observation(g["observation"][i], first), state, cfg, agent.tape, ev, meta["A"])
             np.testing.assert_allclose(a.numpy(), g["actions"][i], rtol=0, atol=2e-6, err_msg=f"step {i}")
     assert agent.tape.pos == len(agent.tape.items)
+
+
+def seeded_init_for(meta):
+    """initial parameters of a slim fixture: the mirror built on CPU under the recorded seed (module creation order = the reference's),
+    verified against the sha256 of the reference's initial state_dict stored in the fixture's json"""
+    import hashlib
+    from genrl_b200.agent.genrl import GenRLAgent
+    from genrl_b200.config import genrl_config, make_specs, Spec
+    cfg = genrl_config(device="cpu", precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent=meta["kind"],
+                       **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    for k, d in meta.get("extra_obs", {}).items():
+        obs_space[k] = Spec((d,), "float32")
+    torch.manual_seed(meta["seed_init"])
+    init = {k: v.detach().clone() for k, v in GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec).state_dict().items()}
+    sha = hashlib.sha256()
+    for k in sorted(init):
+        sha.update(k.encode()); sha.update(init[k].numpy().tobytes())
+    assert sha.hexdigest() == meta["init_sha256"], "seeded initial parameters differ from the reference's"
+    return init
+
+
+def test_oracle_matches_reference_golden_kitchen_shaped_single_sequence():
+    """BASELINE configs[3] flavour at the ragged edge: A = 9, an extra `state` observation key the model ignores, B = 1 sequence with resets.
+    Slim fixture (no parameter dumps): outputs of both updates, bit-exact sample indices and every metric (losses, grad norms) are compared."""
+    torch.set_num_threads(1)
+    g, meta, cfg = load_case("tiny_kitchen")
+    assert not g["init"] and meta["B"] == 1 and "state" in g["data"]
+    agent = O.OracleAgent(seeded_init_for(meta), cfg, kind=meta["kind"])
+    agent.tape = O.NoiseTape(replay=g["tape"])
+    for step in range(2):
+        state, outs, mets = agent.update(g["data"])
+        ref = g[f"ref{step}"]
+        for grp in ("post", "prior"):
+            assert torch.equal(outs[grp]["stoch"], ref[f"outputs/{grp}/stoch"]), (step, grp)
+            for k in ("deter", "logit"):
+                torch.testing.assert_close(outs[grp][k], ref[f"outputs/{grp}/{k}"], rtol=2e-5, atol=1e-6)
+        for k in ("embed", "feat", "kl"):
+            torch.testing.assert_close(outs[k], ref[f"outputs/{k}"], rtol=2e-5, atol=2e-6)
+        for k, v in meta["metrics"][step].items():
+            np.testing.assert_allclose(float(mets[k]), v, rtol=1e-4, atol=1e-6, err_msg=k)
+    assert agent.tape.pos == len(agent.tape.items)
