@@ -231,3 +231,39 @@ def test_oracle_matches_reference_golden_kitchen_shaped_single_sequence():
         for k, v in meta["metrics"][step].items():
             np.testing.assert_allclose(float(mets[k]), v, rtol=1e-4, atol=1e-6, err_msg=k)
     assert agent.tape.pos == len(agent.tape.items)
+
+
+def test_sharded_gradients_average_to_the_global_batch_gradient():
+    """SURVEY §8e (why data parallelism needs only a gradient all-reduce): every loss on the path is a mean of per-row terms, so the
+    average of the shard gradients — each shard seeing its rows of the batch AND its rows of every random draw — equals the gradient of
+    the global batch.  Checked with the oracle for the world-model and the connector gradients of one update, 2 shards x 2 sequences."""
+    torch.set_num_threads(1)
+    g, meta, cfg = load_case("tiny_genrl")
+    B, world = 4, 2
+    data = O.synthetic_batch(B, 16, meta["A"], clip_dim=meta["clip"], seed=21, resets=0.1)
+    glob = O.OracleAgent(g["init"], cfg, kind="genrl")
+    torch.manual_seed(3)
+    glob.update_wm(data)
+    ref = {"wm": glob.last_wm_grads, "connector": glob.last_connector_grads}
+    acc = {"wm": {}, "connector": {}}
+    per = B // world
+    for r in range(world):
+        items = []
+        for kind, v in glob.tape.items:
+            if kind == "randint":
+                items.append((kind, v))
+            else:                                         # draws are batch-major in their leading dimension
+                rows = v.shape[0] // B
+                items.append((kind, v[r * per * rows:(r + 1) * per * rows]))
+        shard = O.OracleAgent(g["init"], cfg, kind="genrl")
+        shard.tape = O.NoiseTape(replay=items)
+        shard.update_wm({k: v[r * per:(r + 1) * per] for k, v in data.items()})
+        assert shard.tape.pos == len(items)
+        for name, grads in (("wm", shard.last_wm_grads), ("connector", shard.last_connector_grads)):
+            for k, v in grads.items():
+                acc[name][k] = acc[name].get(k, 0) + v / world
+    for name in ref:
+        assert set(ref[name]) == set(acc[name])
+        for k, v in ref[name].items():
+            s = float(v.abs().max()) + 1e-12
+            torch.testing.assert_close(acc[name][k] / s, v / s, rtol=0, atol=2e-5, msg=lambda m: f"{name} {k}: {m}")
