@@ -260,11 +260,6 @@ def test_large_rssm_config_runs_on_the_op_level_path():
     assert vals["model_loss"] < first["model_loss"]          # three updates on the same batch reduce the world-model loss
 
 
-import os as _os
-
-
-@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
-                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
 def test_agent_vlm_reward_imag_behavior_matches_reference_golden_fp32():
     """SURVEY §8 a19/a20 on the CUDA path: cached connector target, video_text_reward and update_imag_behavior vs the reference's golden
     vectors (tests/golden/tiny_genrl_vlm.*, pinned on CPU by tests/test_oracle_golden.py)."""
@@ -306,8 +301,6 @@ def test_agent_vlm_reward_imag_behavior_matches_reference_golden_fp32():
     ops.set_noise(ops.PhiloxNoise(0))
 
 
-@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
-                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
 def test_agent_report_videos_match_reference_golden_fp32():
     """SURVEY §8 f3 on the CUDA path: DreamerAgent.report / GenRLAgent.report vs the reference's golden videos
     (tests/golden/tiny_genrl_report.*, pinned on CPU by tests/test_oracle_golden.py)."""
@@ -333,8 +326,6 @@ def test_agent_report_videos_match_reference_golden_fp32():
     ops.set_noise(ops.PhiloxNoise(0))
 
 
-@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
-                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
 def test_agent_act_matches_reference_golden_fp32():
     """SURVEY §8 f4 on the CUDA path: agent.act() over the reference's 6-step episode (tests/golden/tiny_genrl_act.*)."""
     from genrl_b200 import ops
@@ -356,8 +347,6 @@ def test_agent_act_matches_reference_golden_fp32():
     ops.set_noise(ops.PhiloxNoise(0))
 
 
-@pytest.mark.skipif(_os.environ.get("GENRL_EXTRA_GOLDEN") != "1",
-                    reason="written after the round-1 GPU budget was spent (never run on a GPU yet); enable with GENRL_EXTRA_GOLDEN=1")
 def test_agent_update_matches_reference_golden_kitchen_shaped_single_sequence_fp32():
     """tests/golden/tiny_kitchen.* on the CUDA path: A = 9, extra `state` key, B = 1 sequence with resets (slim fixture: outputs + metrics)."""
     from genrl_b200 import ops
