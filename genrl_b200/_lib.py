@@ -59,9 +59,16 @@ class _Lib:
     def load(self):
         if self._dll is not None:
             return self._dll
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
+        # always go through build(): a no-op when build.stamp matches the digest of csrc/ + the header, a rebuild when the library
+        # is missing or stale (a stale binary with a changed argument list but the same symbol names would otherwise be called
+        # with the wrong arguments and never be detected)
+        from . import build as _build
+        try:
             _build.build()
+        except Exception as e:
+            if not os.path.exists(LIB_PATH):
+                raise GenrlError(f"{LIB_PATH} is missing and could not be built ({e}); the genrl_b200 CUDA path has no fallback")
+            raise GenrlError(f"{LIB_PATH} is stale (csrc/ or include/ changed) and could not be rebuilt: {e}")
         if not os.path.exists(LIB_PATH):
             raise GenrlError(f"{LIB_PATH} is missing and could not be built; the genrl_b200 CUDA path has no fallback")
         dll = ctypes.CDLL(LIB_PATH)

@@ -58,8 +58,10 @@ class DreamerAgent(Module):
         self.requires_grad_(requires_grad=False)
         self._store = None
         self._store_sig = None
+        self._moment_bank = None
         self._graphs = {}
         self.dp = None                      # genrl_b200.dist.DataParallel when running one process per GPU
+        self.wm._owner = [self]             # lets train.py's direct wm.* calls (train.py:277-280) reach ensure_store()
 
     # ---- flat parameter store (lazy: train.py swaps sub-modules after construction) ----
     def _param_groups(self):
@@ -86,22 +88,25 @@ class DreamerAgent(Module):
         sig = tuple((k, tuple(id(p) for p in v[0])) for k, v in groups.items())
         if self._store is not None and sig == self._store_sig:
             return self._store
-        old = self._store
-        saved = getattr(self, "_store_state", None)
+        # Adam moments follow the PARAMETERS (in the reference every ActorCritic / WorldModel owns its torch Adam), not the group
+        # name: after finetune_mode() the group "_acting_behavior.actor" holds the imagination behaviour's parameters and must
+        # inherit that behaviour's moments.  Bank = {ids of the group's parameters: (m, v, state)} from the previous store and
+        # from an unpickled snapshot (bound to identities in __setstate__).
+        bank = dict(getattr(self, "_moment_bank", None) or {})
+        if self._store is not None:
+            for og in self._store.groups.values():
+                if og.trainable:
+                    bank[tuple(id(p) for p in og.params)] = (og.m, og.v, og.state)
         store = ParamStore(self.device, _compute_dtype(self.cfg))
         with ops.use_dtype(store.compute_dtype):
             for k, (params, trainable) in groups.items():
                 g = store.add_group(k, params, trainable)
-                prev = None
-                if old is not None and k in old.groups and old.groups[k].numel == g.numel and trainable:
-                    og = old.groups[k]
-                    prev = (og.m, og.v, og.state)
-                elif saved is not None and k in saved and saved[k][0].numel() == g.numel and trainable:
-                    prev = saved[k]
-                if prev is not None:
+                prev = bank.get(tuple(id(p) for p in params)) if trainable else None
+                if prev is not None and prev[0].numel() == g.numel:
                     g.m.copy_(prev[0]); g.v.copy_(prev[1]); g.state.copy_(prev[2])
         self._store, self._store_sig = store, sig
-        self._store_state = None
+        self._moment_bank = None
+        self.wm._owner = [self]
         self._graphs = {}                   # captured graphs hold pointers into the old flat buffers
         opts = [self.wm.model_opt]
         for attr in ("_acting_behavior", "_imag_behavior"):
@@ -120,9 +125,26 @@ class DreamerAgent(Module):
         state["_store_sig"] = None
         state["_graphs"] = {}
         state["dp"] = None
+        state["_moment_bank"] = None
         if st is not None:
             state["_store_state"] = {k: (g.m.clone(), g.v.clone(), g.state.clone()) for k, g in st.groups.items() if g.trainable}
+        elif getattr(self, "_moment_bank", None):
+            groups = self._param_groups()
+            state["_store_state"] = {k: self._moment_bank[tuple(id(p) for p in ps)] for k, (ps, tr) in groups.items()
+                                     if tr and tuple(id(p) for p in ps) in self._moment_bank}
         return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        # bind the snapshot's optimizer state (saved per group name) to the identities of the just-restored parameters, so that
+        # later attribute swaps (finetune_mode, train.py:142-157) cannot hand it to a different module
+        saved = self.__dict__.pop("_store_state", None)
+        self._moment_bank = None
+        if saved:
+            groups = self._param_groups()
+            self._moment_bank = {tuple(id(p) for p in ps): saved[k] for k, (ps, tr) in groups.items() if tr and k in saved}
+        if getattr(self, "wm", None) is not None:
+            self.wm._owner = [self]
 
     def _ctx(self):
         return ops.use_dtype(_compute_dtype(self.cfg))
@@ -278,6 +300,13 @@ class WorldModel(Module):
 
     def update(self, data, state=None):
         """reference dreamer.py:166-187"""
+        self._in_agent_call = True
+        try:
+            return self._update(data, state)
+        finally:
+            self._in_agent_call = False
+
+    def _update(self, data, state=None):
         self.train()
         overlap = getattr(self.cfg, "overlap_streams", False) in (True, "wm") and len(self.detached_update_fns) > 0 and not self.e2e_update_fns
         if overlap:
@@ -315,7 +344,11 @@ class WorldModel(Module):
                     det.append((k, add_loss, add_metrics))
             self.model_opt.backward(model_loss)
             main.wait_stream(side)
-            metrics.update(self.model_opt.apply(model_loss, self.parameters()))
+            # the reference steps the world model on model_loss' gradients alone (dreamer.py:183); the detached modules' gradients are
+            # already in their flat buffers here, so they are excluded from this norm / clip / Adam pass (they still get the
+            # multiplicative weight decay every handed-in parameter receives, dreamer_utils.py:926-932) and stepped below with their own norm
+            det_ids = {id(p) for k in self.detached_update_fns for p in getattr(self, k).parameters()}
+            metrics.update(self.model_opt.apply(model_loss, self.parameters(), active=[p for p in self.parameters() if id(p) not in det_ids]))
             for k, add_loss, add_metrics in det:
                 metrics.update(add_metrics)
                 opt_metrics = self.model_opt.apply(add_loss, getattr(self, k).parameters())
@@ -325,6 +358,7 @@ class WorldModel(Module):
     def update_additional_detached_modules(self, data, outputs, metrics):
         """reference dreamer.py:189-200"""
         detached_loss = 0
+        self._ensure_store()
         with ops.use_dtype(_compute_dtype(self.cfg)):
             for k in self.detached_update_fns:
                 detached_module = getattr(self, k)
@@ -335,6 +369,17 @@ class WorldModel(Module):
                     metrics.update({f"{k}_{m}": opt_metrics[m] for m in opt_metrics})
         return detached_loss, metrics
 
+    def _ensure_store(self):
+        """train.py calls wm.observe_data / wm.update_additional_detached_modules directly (train.py:277-280): make sure the flat
+        parameter store exists (and a fresh Philox key is drawn when no update call of the agent did it)"""
+        owner = getattr(self, "_owner", None)
+        if owner and owner[0] is not None:
+            owner[0].ensure_store()
+            if not getattr(self, "_in_agent_call", False):
+                ops.noise_tick(self.device)
+        elif self.model_opt.store is None:
+            raise RuntimeError("WorldModel is not attached to an agent: call agent.ensure_store() first")
+
     def update_additional_e2e_modules(self, data, outputs, model_loss, metrics):
         for k in self.e2e_update_fns:
             add_loss, add_metrics = self.e2e_update_fns[k](self, k, data, outputs, metrics)
@@ -344,7 +389,8 @@ class WorldModel(Module):
 
     def observe_data(self, data, state=None):
         """reference dreamer.py:210-217"""
-        with ops.use_dtype(_compute_dtype(self.cfg)):
+        self._ensure_store()
+        with torch.no_grad(), ops.use_dtype(_compute_dtype(self.cfg)):
             embed = self.encoder(data)
             post, prior = self.rssm.observe(embed, data["action"], data["is_first"], state)
             kl_loss, kl_value = self.rssm.kl_loss(post, prior, **self.cfg.kl)
@@ -468,6 +514,11 @@ class ActorCritic(Module):
                 p.data = p.data * 0
         for s, d in zip(self.critic.parameters(), self._target_critic.parameters()):
             d.data = s.data.clone()
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("dp_gather", None)        # bound to a process group; re-attached by DataParallel.attach after a resume
+        return state
 
     def update(self, world_model, start, is_terminal, reward_fn, slow_target=True):
         """reference dreamer.py:366-390"""

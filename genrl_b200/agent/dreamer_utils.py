@@ -664,11 +664,21 @@ class Optimizer:
         assert len(loss.shape) == 0 or (len(loss.shape) == 1 and loss.shape[0] == 1), (self._name, loss.shape)
         loss.backward()
 
-    def apply(self, loss, params):
-        """grad-norm / clip / weight decay / Adam on the groups of `params` (the backward has already run)"""
+    def __getstate__(self):
+        # snapshots (train.py pickles the whole agent) must not carry the flat store (params, grads, moments, shadows: several
+        # times the model size) nor a process-group hook; the agent re-attaches both in ensure_store()
+        state = self.__dict__.copy()
+        state["store"] = None
+        state["allreduce"] = None
+        return state
+
+    def apply(self, loss, params, active=None):
+        """grad-norm / clip / weight decay / Adam on the groups of `params` (the backward has already run).  `active` restricts the
+        norm / clip / Adam part to the groups of those parameters; the other groups of `params` only get the weight decay."""
         metrics = {f"{self._name}_loss": loss.detach()}
         groups = self.store.groups_of(list(params))
-        norm = self.store.step(groups, self._lr, self._eps, self._clip, self._wd, self.allreduce)
+        only = None if active is None else self.store.groups_of(list(active))
+        norm = self.store.step(groups, self._lr, self._eps, self._clip, self._wd, self.allreduce, only=only)
         if self._clip:
             metrics[f"{self._name}_grad_norm"] = norm
         return metrics

@@ -22,7 +22,11 @@ def _digest():
     h = hashlib.sha256()
     for f in _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")):
         h.update(open(f, "rb").read())
-    h.update(" ".join(FLAGS).encode())
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    for f in sorted(os.listdir(inc)):
+        h.update(open(os.path.join(inc, f), "rb").read())
+    # location-independent: the repo is snapshotted to a scratch path on the GPU box and the prebuilt library must count as current
+    h.update(" ".join(x for x in FLAGS if x != inc).encode())
     return h.hexdigest()
 
 

@@ -135,12 +135,12 @@ class ParamStore:
         for g in self.groups.values():
             g.refresh()
 
-    def step(self, groups, lr, eps, clip, wd, allreduce=None):
+    def step(self, groups, lr, eps, clip, wd, allreduce=None, only=None):
         """clip_grad_norm_ -> weight decay on every group handed in -> Adam on the groups that received gradients.
 
         Returns the device scalar holding the (pre-clip) gradient norm."""
         st = ops._st()
-        active = [g for g in groups if g.trainable and g.touched]
+        active = [g for g in groups if g.trainable and g.touched and (only is None or any(g is o for o in only))]
         if allreduce is not None and active:
             allreduce([g.grad for g in active])
         first = True

@@ -104,8 +104,12 @@ def test_agent_fast_noise_pickle_and_act():
     assert all(np.isfinite(float(torch.as_tensor(v).float().cpu().reshape(-1)[0])) for v in metrics.values())
     buf = io.BytesIO()
     torch.save({"agent": agent}, buf)                       # train.py:387-398 pickles the whole agent
+    # the snapshot carries parameters + Adam moments once (no flat gradient buffers, weight shadows or duplicate stores)
+    pbytes = sum(p.numel() * 4 for p in agent.parameters())
+    assert buf.tell() <= 3.4 * pbytes + (1 << 20), f"snapshot {buf.tell()} bytes for {pbytes} parameter bytes"
     buf.seek(0)
     agent2 = torch.load(buf, weights_only=False)["agent"]
+    assert agent2.wm.model_opt.store is None and not hasattr(agent2._acting_behavior, "dp_gather")
     for (k, a), (_, b) in zip(agent.state_dict().items(), agent2.state_dict().items()):
         assert torch.equal(a, b), k
     state2, metrics2 = agent2.update(data, 1)
@@ -171,6 +175,81 @@ def test_overlapped_streams_match_single_stream():
     for h in b:
         assert all(np.isfinite(v) for v in h.values())
     assert b[3]["model_loss"] < b[0]["model_loss"]
+    ops.set_noise(ops.PhiloxNoise(0))
+
+
+def test_overlapped_connector_step_has_its_own_norm_and_matches_single_stream():
+    """with overlap_streams the connector's gradients are already in their flat buffer when the world-model step
+    runs; they must not enter the world-model norm / clip / Adam pass.  One update_wm: connector_model_grad_norm > 0 and equal to the
+    single-stream schedule's, model_grad_norm equal, connector weights equal (the only difference left is the 1e-6 decay order)."""
+    from genrl_b200 import ops
+    res = []
+    for overlap in (False, True):
+        agent, data, g, meta = build_agent("tiny_genrl", 32)
+        agent.cfg.overlap_streams = overlap
+        ops.set_noise(ops.PhiloxNoise(9))
+        state, outputs, metrics = agent.update_wm(data, 0)
+        res.append(({k: float(torch.as_tensor(v).float().cpu().reshape(-1)[0]) for k, v in metrics.items()},
+                    {k: v.clone() for k, v in agent.wm.connector.state_dict().items()}))
+    (m0, c0), (m1, c1) = res
+    assert m1["connector_model_grad_norm"] > 0
+    for k in ("connector_model_grad_norm", "model_grad_norm", "connector_model_loss", "model_loss"):
+        assert abs(m0[k] - m1[k]) <= 1e-4 * max(1.0, abs(m0[k])), (k, m0[k], m1[k])
+    for k in c0:
+        assert torch.allclose(c0[k], c1[k], rtol=1e-4, atol=2e-6), k
+    ops.set_noise(ops.PhiloxNoise(0))
+
+
+def test_finetune_mode_keeps_the_imag_behaviours_adam_state():
+    """after finetune_mode() the acting behaviour IS the imagination behaviour; its flat group must inherit that
+    behaviour's Adam moments (the reference's per-module torch Adam follows the module), not the old acting behaviour's."""
+    from genrl_b200 import ops
+    from tests.test_oracle_golden import _load_vlm_case
+    from genrl_b200.agent.genrl import GenRLAgent
+    g, meta, _ = _load_vlm_case()
+    cfg = genrl_config(device=DEV, precision=32, batch_size=meta["B"], batch_length=meta["T"], imag_horizon=meta["H"], agent="genrl",
+                       **meta["overrides"])
+    obs_space, act_spec = make_specs(action_dim=meta["A"], clip_dim=meta["clip"])
+    torch.manual_seed(1)
+    agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
+    agent.load_state_dict(g["init"], strict=True)
+    agent.unconditional_target = {k: v.to(DEV) for k, v in g["target"].items()}
+    data = {k: v.to(DEV) for k, v in g["data"].items()}
+    ops.set_noise(ops.PhiloxNoise(3))
+    state, outputs, metrics = agent.update_wm(data, 0)
+    agent.update_imag_behavior(state, outputs, metrics, seq_data=data)
+    agent.update_acting_behavior(state, outputs, metrics, data)
+    st = agent.ensure_store()
+    m_imag = st.groups["_imag_behavior.actor"].m.clone()
+    m_act = st.groups["_acting_behavior.actor"].m.clone()
+    assert float(m_imag.abs().sum()) > 0 and not torch.equal(m_imag, m_act)
+    # through a snapshot as well: the state saved under the group name must follow the module, not the name
+    buf = io.BytesIO(); torch.save({"agent": agent}, buf); buf.seek(0)
+    for ag in (agent, torch.load(buf, weights_only=False)["agent"]):
+        ag.finetune_mode()
+        st2 = ag.ensure_store()
+        assert "_imag_behavior.actor" not in st2.groups
+        assert torch.equal(st2.groups["_acting_behavior.actor"].m, m_imag)
+        assert float(st2.groups["_acting_behavior.actor"].state[0]) == 1.0
+    ops.set_noise(ops.PhiloxNoise(0))
+
+
+def test_direct_wm_calls_of_train_py_work_without_a_prior_update():
+    """train.py:277-280 (train_world_model: False, train_connector: True): wm.observe_data + wm.update_additional_detached_modules are
+    the first calls on a fresh agent; they must build the flat store themselves and step the connector only."""
+    from genrl_b200 import ops
+    agent, data, g, meta = build_agent("tiny_genrl", 32)
+    ops.set_noise(ops.PhiloxNoise(4))
+    before = {k: v.clone() for k, v in agent.state_dict().items()}
+    with torch.no_grad():
+        outputs, metrics = agent.wm.observe_data(data)
+    assert set(outputs) >= {"embed", "post", "prior", "is_terminal"} and np.isfinite(float(metrics["model_kl"]))
+    _, metrics = agent.wm.update_additional_detached_modules(data, outputs, metrics)
+    assert float(metrics["connector_model_grad_norm"]) > 0
+    after = agent.state_dict()
+    changed = {k for k in before if not torch.equal(before[k], after[k])}
+    assert any(k.startswith("wm.connector.") for k in changed)
+    assert all(k.startswith("wm.connector.") for k in changed), sorted(changed)[:5]
     ops.set_noise(ops.PhiloxNoise(0))
 
 
