@@ -38,6 +38,12 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
+    ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: fp16 autocast (the reference's precision: 16)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: sample size in sequences (default REF_SAMPLE_B)")
+    ap.add_argument("--sequence", default="S2", choices=["S1", "S2", "S3"],
+                    help="S1 update_wm; S2 update_wm + update_acting_behavior (default, BASELINE configs[1]); S3 train.py:275,280,340 "
+                         "(update_wm + second connector step + update_imag_behavior with the VLM reward)")
     return ap.parse_args()
 
 
@@ -95,7 +101,8 @@ class ClockSampler:
 
 def make_cfg(args, device, precision):
     from genrl_b200.config import genrl_config, make_specs
-    cfg = genrl_config(device=device, precision=precision, batch_size=args.batch, batch_length=args.length, imag_horizon=args.horizon)
+    over = {"imag_reward_fn": "video_text_reward"} if getattr(args, "sequence", "S2") == "S3" else {}
+    cfg = genrl_config(device=device, precision=precision, batch_size=args.batch, batch_length=args.length, imag_horizon=args.horizon, **over)
     obs_space, act_spec = make_specs(action_dim=args.action_dim, clip_dim=512)
     return cfg, obs_space, act_spec
 
@@ -106,14 +113,20 @@ def synthetic(B, T, A, seed):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+REF_SAMPLE_B = 25        # fixed sample of the reference arm: half of the workload's 50 sequences, every run, every N
+
+
 def run_reference(args):
-    """the reference algorithm (oracle port: same torch-CPU ops as the reference's own code path) on the host cores"""
+    """The reference algorithm (oracle port: the same torch ops in the same order as the reference's own code path) on the host cores.
+    Fixed sample (REF_SAMPLE_B of the workload's sequences, full T / H / architecture) so the number is comparable across runs.
+    --ref-device cuda runs the same port as torch-eager kernels on the GPU (cuDNN / cuBLAS via torch): the 'existing Blackwell path' bar
+    of BASELINE.md §3 (reported under profiles/, not the driver's reference arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import genrl_oracle as O
-    from genrl_b200.config import genrl_config, make_specs
     from genrl_b200.agent.genrl import GenRLAgent
+    on_gpu = args.ref_device == "cuda"
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     cfg, obs_space, act_spec = make_cfg(args, "cpu", 32)
@@ -121,33 +134,47 @@ def run_reference(args):
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         init = {k: v.detach().clone() for k, v in GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec).state_dict().items()}
-    # bounded sample of the workload: pick the sample batch so the whole run ends within a few minutes
-    probe_B = 2
-    agent = O.OracleAgent(init, cfg, kind="genrl")
-    data = synthetic(probe_B, args.length, args.action_dim, 0)
-    t0 = time.perf_counter(); agent.update(data); per_row = (time.perf_counter() - t0) / probe_B
-    budget = 150.0
-    Bs = int(max(1, min(args.batch, budget / max(per_row, 1e-3) / max(1, args.steps + args.warmup))))
+    Bs = args.batch if on_gpu else min(args.batch, args.ref_batch or REF_SAMPLE_B)
     data = synthetic(Bs, args.length, args.action_dim, 1)
-    for _ in range(args.warmup):
-        agent.update(data)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        agent.update(data)
+    if on_gpu:
+        torch.set_default_device("cuda")
+        init = {k: v.cuda() for k, v in init.items()}
+        data = {k: v.cuda() for k, v in data.items()}
+    agent = O.OracleAgent(init, cfg, kind="genrl")
+    amp = torch.autocast("cuda", dtype=torch.float16) if (on_gpu and args.ref_autocast) else contextlib.nullcontext()
+
+    def sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+    with amp:
+        for _ in range(max(1, args.warmup if on_gpu else min(args.warmup, 1))):
+            agent.update(data)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            agent.update(data)
+        sync()
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = Bs * args.length / dt
-    sample = f"B={Bs} of {args.batch} sequences x T={args.length}, H={args.horizon}, fp32, full update (WM+connector+behaviour)"
+    where = ("torch-eager CUDA kernels on the GPU, " + ("fp16 autocast" if args.ref_autocast else "fp32")) if on_gpu else "fp32 on the host CPU"
+    sample = f"B={Bs} of {args.batch} sequences x T={args.length}, H={args.horizon}, {where}, full update (WM+connector+behaviour)"
     line = {"impl": "reference", "metric": "seq_frames_per_s_full_genrl_update", "value": value, "unit": "seq-frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": (args.warmup if on_gpu else min(args.warmup, 1)), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if (on_gpu and args.ref_autocast) else "f32", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": "seq-frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "seq-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if on_gpu:
+        line["device"] = "cuda (torch eager)"
     print(json.dumps(line))
 
 
+SEQ_TEXT = {"S1": "S1 (update_wm incl. connector)", "S2": "S2 (update_wm incl. connector + update_acting_behavior)",
+            "S3": "S3 (train.py:275,280,340: update_wm + second connector step + update_imag_behavior with the VLM reward)"}
+
+
 def workload_config(args):
-    return {"workload": f"GenRL full update S2 (update_wm incl. connector + update_acting_behavior), stickman A={args.action_dim}, "
+    return {"workload": f"GenRL full update {SEQ_TEXT[args.sequence]}, stickman A={args.action_dim}, "
                         f"per-GPU batch {args.batch}x{args.length}, 64x64x3 u8 obs, deter=1024, stoch=32x32, imag_horizon={args.horizon}",
             "batch": args.batch, "length": args.length, "horizon": args.horizon, "parallelism": f"dp{args.gpus}",
             "l2": "5 rotating input batches (150 MB) and a multi-GB per-step working set exceed the 126 MB L2"}
@@ -196,9 +223,20 @@ def run_native(args):
     devb = [{k: v.to(dev) for k, v in b.items()} for b in host]
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
+    if args.sequence == "S3":
+        # train.py:289-319 caches the connector's rollout from the task prompt once; synthetic stand-in: random one-hot latents
+        Hn, Nn = args.horizon + 1, args.batch * args.length
+        idx = torch.randint(0, 32, (Hn, Nn, 32), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        tgt = torch.nn.functional.one_hot(idx, 32).float()
+        agent.unconditional_target = {"stoch": tgt, "logit": torch.zeros_like(tgt), "deter": torch.zeros(Hn, Nn, 1024, device=dev)}
+
     def step(data, i):
         state, outputs, metrics = agent.update_wm(data, i)
-        start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+        if args.sequence == "S2":
+            start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
+        elif args.sequence == "S3":
+            _, metrics = agent.wm.update_additional_detached_modules(data, outputs, metrics)
+            start, metrics = agent.update_imag_behavior(state, outputs, metrics, seq_data=data)
         return metrics
 
     def barrier():
@@ -269,7 +307,7 @@ def run_native(args):
             "gpu_launches": int(launches), "clocks": clk}
 
     if rank == 0 and world == 1 and not args.no_roofline:
-        line["roofline"], line["kernel_breakdown"] = roofline_pass(step, devb, nb, lib, args, agent)
+        line.update(roofline_pass(step, devb, nb, lib, args, agent, ms_step))
     elif rank == 0 and world > 1:
         # the roofline pass re-runs eager steps on ONE rank; with data parallelism attached those steps contain NCCL collectives
         # the other ranks would never join (it hung an 8-GPU run), and the kernel metric is a single-GPU quantity anyway
@@ -287,80 +325,166 @@ def run_native(args):
         os._exit(0)
 
 
-def roofline_pass(step, devb, nb, lib, args, agent):
-    """Roofline of the dominant kernel (the tcgen05 GEMM: 40 % of the step's GPU time, profiles/).
+def conv_algorithmic_flops(frames, depth=48, img=64):
+    """Algorithmic FLOPs of the conv stacks per update: encoder k4 s2 x4, decoder convT k5,k5,k6,k6 s2.  The decoder's first
+    layer acts on a 1x1 map and runs as a plain GEMM (counted with the GEMMs), the rest on the implicit-GEMM kernels.
+    Returns (fwd-type kernel flops: forward + dgrad, wgrad kernel flops)."""
+    enc, h, cin = [], img, 3
+    for i in range(4):
+        cout, ho = depth * 2 ** i, (h - 4) // 2 + 1
+        enc.append(ho * ho * cout * cin * 16); h, cin = ho, cout                  # MACs per frame
+    dec, h, cin = [], 1, 32 * depth
+    for i, k in enumerate((5, 5, 6, 6)):
+        cout = 3 if i == 3 else depth * 2 ** (2 - i)
+        dec.append(h * h * cin * cout * k * k); h, cin = (h - 1) * 2 + k, cout
+    fwd = sum(enc) + sum(dec[1:])
+    dgrad = sum(enc[1:]) + sum(dec[1:])                                           # no gradient to the pixels
+    wgrad = sum(enc) + sum(dec[1:])
+    return 2.0 * frames * (fwd + dgrad), 2.0 * frames * wgrad
 
-    1. two instrumented EAGER steps with CUDA events on the launching stream around every C-ABI call give each entry point's share
-       of the step (the graph-captured steps of the timed region cannot be instrumented per kernel);
-    2. every distinct GEMM call of the step (shape, operand majors, dtypes, accumulate) is then replayed on fresh operands, R launches
-       back to back between two CUDA events, so the per-launch duration excludes the ~8 us event/launch floor that dominates
-       a 10 us kernel when it is timed alone.  achieved = sum(2MNK x calls) / sum(duration x calls)."""
-    from genrl_b200 import ops
+
+def rssm_algorithmic_bytes(B, T, A, E=1536, S=32, K=32, D=1024, Hd=1024, s=4, s_w=4):
+    """SURVEY §8d 'Algorithmic bytes - RSSM observe fwd': (compulsory, streamed)."""
+    N = B * T
+    io = N * (E + A + 1) * s + N * (4 * S * K + D) * s
+    p_rec = (S * K + A) * Hd + (Hd + D) * 3 * D + D * Hd + Hd * S * K
+    p_post = E * Hd + Hd * S * K
+    return io + (p_rec + p_post) * s_w, io + p_post * s_w + T * p_rec * s_w
+
+
+def cupti_kernels(fn, n):
+    """per-kernel device durations (CUPTI via torch.profiler) of n calls of fn, graph replays included; {name: [launches, us]}"""
+    import collections, re
+    from torch.profiler import profile, ProfilerActivity
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(n):
+            fn(i)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for e in prof.events():
+        if e.device_type.name != "CUDA":
+            continue
+        name = re.sub(r"\(.*", "", re.sub(r"<.*", "", e.name)).replace("void ", "").strip()
+        t = e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+        agg[name][0] += 1; agg[name][1] += t
+    return agg
+
+
+def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
+    """Rooflines of the three kernel families BASELINE's metric names, measured LIVE on the graph-replayed steps of the timed
+    configuration: per-kernel device durations come from CUPTI (torch.profiler) over n replayed steps, algorithmic work from the
+    arguments of the C-ABI calls one eager step makes (GEMM: 2MNK) or from the layer table (conv stacks).
+      roofline       tcgen05 GEMM family (dominant: largest share of the step)  -> tensor roofline, measured sustained bf16 peak
+      roofline_conv  implicit-GEMM conv kernels                                 -> tensor roofline
+      roofline_rssm  persistent scan kernel + the whole observe() forward       -> HBM roofline, §8d compulsory and streamed bytes"""
     pk = peaks()
+    bf16 = args.precision == 16
+    # 1. work of one step, from one instrumented eager step (no timing taken here)
     graphs_on, agent.cfg.cuda_graph = agent.cfg.cuda_graph, False
+    counts = {"gemm_flops": 0.0, "gemm_calls": 0, "scan_calls": 0}
+    hooks = {}
+
+    def hook(name, fn):
+        orig = getattr(lib, name)
+        hooks[name] = orig
+        def wrapped(*a):
+            fn(a)
+            return orig(*a)
+        lib.__dict__[name] = wrapped
+    def on_gemm(a):
+        counts["gemm_flops"] += 2.0 * a[1] * a[2] * a[3]; counts["gemm_calls"] += 1
+    hook("genrl_gemm", on_gemm)
+    hook("genrl_gemm_ln_fwd", on_gemm)
+    hook("genrl_rssm_scan_fwd", lambda a: counts.__setitem__("scan_calls", counts["scan_calls"] + 1))
     step(devb[0], 0)
     torch.cuda.synchronize()
-    lib.profile = []
-    n = 2
-    for i in range(n):
-        step(devb[i % nb], i)
-    torch.cuda.synchronize()
-    prof, lib.profile = lib.profile, None
+    for k, v in hooks.items():
+        lib.__dict__[k] = v
     agent.cfg.cuda_graph = graphs_on
-    agg, shapes = {}, {}
-    for name, e0, e1, a, allargs in prof:
-        d = agg.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})
-        d["ms"] += e0.elapsed_time(e1); d["calls"] += 1
-        if name == "genrl_gemm":
-            d["flops"] += 2.0 * a[0] * a[1] * a[2]
-            key = (allargs[1], allargs[2], allargs[3], allargs[6], allargs[9], allargs[10], allargs[13], allargs[15], allargs[14] is not None)
-            shapes[key] = shapes.get(key, 0) + 1
-    total = sum(d["ms"] for d in agg.values())
-    breakdown = {k: {"ms_per_step": v["ms"] / n, "calls_per_step": v["calls"] // n, "share": v["ms"] / total} for k, v in
-                 sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:8]}
-    g = agg.get("genrl_gemm")
+    for i in range(3):                      # back on the captured graphs (the eager step dropped nothing, but re-warm anyway)
+        step(devb[i % nb], i)
+    # 2. CUPTI durations over replayed steps
+    n = 3
+    agg = cupti_kernels(lambda i: step(devb[i % nb], i), n)
+    total_us = sum(v[1] for v in agg.values())
+    breakdown = {k: {"ms_per_step": v[1] / n / 1e3, "launches_per_step": v[0] / n, "avg_us": v[1] / v[0], "share_of_kernel_time": v[1] / total_us}
+                 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]}
+    breakdown["_total"] = {"kernel_ms_per_step": total_us / n / 1e3, "launches_per_step": sum(v[0] for v in agg.values()) / n,
+                           "step_ms": ms_step, "source": f"CUPTI (torch.profiler) over {n} graph-replayed steps"}
+    fam = lambda *pats: [sum(v[0] for k, v in agg.items() if any(p in k for p in pats)), sum(v[1] for k, v in agg.items() if any(p in k for p in pats))]
+    g_l, g_us = fam("gemm_tc_kernel", "gemm_tc_persist_kernel", "gemm_ln_kernel", "gemm_simt_kernel")
     roof = None
-    if g and g["ms"] > 0:
-        dev = devb[0]["action"].device
-        st = torch.cuda.current_stream()
-        flops = dur_ms = 0.0
-        R = 20
-        for (M, N, K, tA, tW, in_dt, c_dt, acc, has_bias), cnt in shapes.items():
-            idt = torch.bfloat16 if in_dt == 1 else torch.float32
-            cdt = torch.bfloat16 if c_dt == 1 else torch.float32
-            pad = lambda v: (v + 7) // 8 * 8
-            A = torch.randn((K, pad(M)) if tA else (M, pad(K)), device=dev).to(idt)
-            W = torch.randn((K, pad(N)) if tW else (N, pad(K)), device=dev).to(idt)
-            C = torch.zeros(M, pad(N), device=dev, dtype=cdt)
-            bias = torch.zeros(N, device=dev) if has_bias else None
-            call = lambda: lib.genrl_gemm(st.cuda_stream, M, N, K, A.data_ptr(), A.stride(0), tA, W.data_ptr(), W.stride(0), tW, in_dt,
-                                          C.data_ptr(), C.stride(0), c_dt, None if bias is None else bias.data_ptr(), acc)
-            call(); call()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record(st)
-            for _ in range(R):
-                call()
-            e1.record(st)
-            torch.cuda.synchronize()
-            per = e0.elapsed_time(e1) / R
-            flops += 2.0 * M * N * K * cnt
-            dur_ms += per * cnt
-        achieved = flops / (dur_ms * 1e-3) / 1e12
-        bf16 = args.precision == 16
+    if g_us > 0:
+        achieved = counts["gemm_flops"] * n / (g_us * 1e-6) / 1e12
         peak = pk["tf_sustained"] if bf16 else 75.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if bf16 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")      # ncu dram__bytes_read+write, mean over the step's GEMM launches
-        calls = sum(shapes.values())
-        roof = {"kernel": "gemm_tc_kernel (tcgen05)" if bf16 else "gemm_simt_kernel (fp32 parity mode)", "bound": "tensor", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        roof = {"kernel": "gemm_tc_kernel + gemm_tc_persist_kernel + gemm_ln_kernel (tcgen05)" if bf16 else "gemm_simt_kernel (fp32 parity mode)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": (pk["source"] + " bf16 sustained") if bf16 else "nominal fp32 FFMA",
-                "share_of_step": g["ms"] / total, "launch_avg_us": dur_ms / calls * 1e3, "launches_per_step": calls // n,
-                "algorithmic_flops_per_launch": flops / calls, "algorithmic_flops_per_step": flops / n,
-                "method": f"{len(shapes)} distinct GEMM calls of the step replayed {R}x back to back between CUDA events"}
-    return roof, breakdown
+                "share_of_step": g_us / total_us, "launch_avg_us": g_us / g_l, "launches_per_step": g_l / n,
+                "algorithmic_flops_per_launch": counts["gemm_flops"] * n / g_l, "algorithmic_flops_per_step": counts["gemm_flops"],
+                "method": f"sum of 2MNK over the step's {counts['gemm_calls']} GEMM calls / sum of their CUPTI kernel durations inside {n} graph-replayed steps"}
+    out = {"roofline": roof, "kernel_breakdown": breakdown}
+    # conv stacks
+    frames = args.batch * args.length
+    f_fwd, f_wg = conv_algorithmic_flops(frames)
+    c_l, c_us = fam("conv_fwd_kernel")
+    w_l, w_us = fam("conv_wgrad_kernel")
+    if bf16 and c_us > 0 and w_us > 0:
+        peak = pk["tf_sustained"]
+        out["roofline_conv"] = {
+            "bound": "tensor", "unit": "TFLOP/s", "peak": peak, "peak_source": pk["source"] + " bf16 sustained",
+            "fwd_dgrad": {"kernel": "conv_fwd_kernel (implicit GEMM, tcgen05)", "launches_per_step": c_l / n, "ms_per_step": c_us / n / 1e3,
+                          "algorithmic_flops_per_step": f_fwd, "achieved": f_fwd * n / (c_us * 1e-6) / 1e12, "frac": f_fwd * n / (c_us * 1e-6) / 1e12 / peak},
+            "wgrad": {"kernel": "conv_wgrad_kernel (implicit GEMM, tcgen05)", "launches_per_step": w_l / n, "ms_per_step": w_us / n / 1e3,
+                      "algorithmic_flops_per_step": f_wg, "achieved": f_wg * n / (w_us * 1e-6) / 1e12, "frac": f_wg * n / (w_us * 1e-6) / 1e12 / peak},
+            "achieved": (f_fwd + f_wg) * n / ((c_us + w_us) * 1e-6) / 1e12, "frac": (f_fwd + f_wg) * n / ((c_us + w_us) * 1e-6) / 1e12 / peak,
+            "tensor_pipe_util": "ncu sm__pipe_tensor* per launch: profiles/ (conv digest)"}
+    # RSSM
+    s_l, s_us = fam("rssm_scan_fwd_kernel")
+    if s_us > 0:
+        B, T, D = args.batch, args.length, 1024
+        N = B * T
+        sa = 2 if bf16 else 4
+        # what the scan kernel itself has to move once: gx in (fp32), deter out (fp32), m*h_prev out (compute dtype), pre-activations z
+        # and LayerNorm statistics out (saved for the backward), the W_h slice in (fp32 master, converted on load)
+        kbytes = N * 3 * D * 4 + N * D * 4 + N * D * sa + N * 3 * D * 4 + N * 2 * 4 + 3 * D * D * 4
+        us = s_us / s_l
+        comp, streamed = rssm_algorithmic_bytes(B, T, args.action_dim)
+        obs_us = time_observe(agent, devb[0])
+        out["roofline_rssm"] = {
+            "kernel": "rssm_scan_fwd_kernel (persistent, one launch per sequence batch)", "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"],
+            "peak_source": pk["source"] + " HBM copy", "launches_per_step": s_l / n, "us_per_launch": us, "us_per_time_step": us / T,
+            "kernel_bytes_per_launch": kbytes, "achieved": kbytes / (us * 1e-6) / 1e9, "frac": kbytes / (us * 1e-6) / 1e9 / pk["hbm"],
+            "observe_fwd": {"what": "whole EnsembleRSSM.observe forward (batched posterior / input / prior GEMMs + LayerNorms + samples + the scan), "
+                                    "eager launches between CUDA events, best of 5", "us": obs_us,
+                            "compulsory_bytes_fp32": comp, "streamed_bytes_fp32": streamed,
+                            "gbs_vs_compulsory": comp / (obs_us * 1e-6) / 1e9, "frac_vs_compulsory": comp / (obs_us * 1e-6) / 1e9 / pk["hbm"],
+                            "gbs_vs_streamed": streamed / (obs_us * 1e-6) / 1e9, "frac_vs_streamed": streamed / (obs_us * 1e-6) / 1e9 / pk["hbm"],
+                            "note": "SURVEY §8d: 'streamed' is the figure when the recurrent weights exceed the 33 MB of aggregate shared memory "
+                                    "(fp32: 37.8 MB) and are re-read every time step; this design keeps the W_h slice resident instead"}}
+    return out
+
+
+def time_observe(agent, data):
+    """device time of one EnsembleRSSM.observe forward at the benchmark shape (no grad), best of 5"""
+    from genrl_b200 import ops
+    best = 1e30
+    with torch.no_grad(), agent._ctx():
+        embed = agent.wm.encoder(data)
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            agent.wm.rssm.observe(embed, data["action"], data["is_first"])
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3)
+    return best
 
 
 def cpu_baseline(args, agent):

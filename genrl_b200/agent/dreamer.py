@@ -320,7 +320,7 @@ class WorldModel(Module):
         outputs = {k: ({kk: vv.detach() for kk, vv in v.items()} if isinstance(v, dict) else v.detach()) for k, v in outputs.items()}
         state = {k: v.detach() for k, v in state.items()}
         if len(self.detached_update_fns) > 0:
-            detached_loss, metrics = self.update_additional_detached_modules(data, outputs, metrics)
+            metrics = self._detached_steps(data, outputs, metrics)
         self.eval()
         return state, outputs, metrics
 
@@ -342,6 +342,8 @@ class WorldModel(Module):
                     add_loss, add_metrics = self.detached_update_fns[k](self, k, data, outputs, metrics)
                     self.model_opt.backward(add_loss)
                     det.append((k, add_loss, add_metrics))
+                    # data parallel: this module's gradients are final -> average them on this stream, beside the world model's backward
+                    self.model_opt.reduce(getattr(self, k).parameters())
             self.model_opt.backward(model_loss)
             main.wait_stream(side)
             # the reference steps the world model on model_loss' gradients alone (dreamer.py:183); the detached modules' gradients are
@@ -356,9 +358,27 @@ class WorldModel(Module):
         return state, outputs, metrics
 
     def update_additional_detached_modules(self, data, outputs, metrics):
-        """reference dreamer.py:189-200"""
+        """reference dreamer.py:189-200.  Called from update() and, by train.py:280, directly (a second connector step per iteration);
+        the direct call draws a fresh Philox key and, with cfg.cuda_graph, is captured into a CUDA graph like the agent's update calls."""
         detached_loss = 0
-        self._ensure_store()
+        if getattr(self, "_in_agent_call", False):
+            return detached_loss, self._detached_steps(data, outputs, metrics)
+        owner = self._ensure_store()
+        with ops.use_dtype(_compute_dtype(self.cfg)):
+            if owner is not None and owner._use_graphs() and set(self.detached_update_fns) <= {"connector"}:
+                used = {"clip_video": data["clip_video"]}
+                post = {k: outputs["post"][k] for k in ("stoch", "logit")}
+                mets = owner._run("detached", self._detached_direct, used, post)
+            else:
+                mets = self._detached_direct(data, outputs["post"])
+        metrics.update(mets)
+        return detached_loss, metrics
+
+    def _detached_direct(self, data, post):
+        ops.noise_tick(self.device)
+        return self._detached_steps(data, {"post": post}, {})
+
+    def _detached_steps(self, data, outputs, metrics):
         with ops.use_dtype(_compute_dtype(self.cfg)):
             for k in self.detached_update_fns:
                 detached_module = getattr(self, k)
@@ -367,18 +387,18 @@ class WorldModel(Module):
                     metrics.update(add_metrics)
                     opt_metrics = self.model_opt(add_loss, detached_module.parameters())
                     metrics.update({f"{k}_{m}": opt_metrics[m] for m in opt_metrics})
-        return detached_loss, metrics
+        return metrics
 
     def _ensure_store(self):
         """train.py calls wm.observe_data / wm.update_additional_detached_modules directly (train.py:277-280): make sure the flat
-        parameter store exists (and a fresh Philox key is drawn when no update call of the agent did it)"""
+        parameter store exists; returns the owning agent"""
         owner = getattr(self, "_owner", None)
         if owner and owner[0] is not None:
             owner[0].ensure_store()
-            if not getattr(self, "_in_agent_call", False):
-                ops.noise_tick(self.device)
-        elif self.model_opt.store is None:
+            return owner[0]
+        if self.model_opt.store is None:
             raise RuntimeError("WorldModel is not attached to an agent: call agent.ensure_store() first")
+        return None
 
     def update_additional_e2e_modules(self, data, outputs, model_loss, metrics):
         for k in self.e2e_update_fns:
@@ -390,6 +410,7 @@ class WorldModel(Module):
     def observe_data(self, data, state=None):
         """reference dreamer.py:210-217"""
         self._ensure_store()
+        ops.noise_tick(self.device)
         with torch.no_grad(), ops.use_dtype(_compute_dtype(self.cfg)):
             embed = self.encoder(data)
             post, prior = self.rssm.observe(embed, data["action"], data["is_first"], state)
@@ -540,6 +561,7 @@ class ActorCritic(Module):
                     seq_d = {k: stop_gradient(v) for k, v in seq.items()}
                     critic_loss, mets4 = self.critic_loss(seq_d, target)
                     self.critic_opt.backward(critic_loss)
+                    self.critic_opt.reduce(self.critic.parameters())      # collective beside the actor's backward
                 self.actor_opt.backward(actor_loss)
                 dg.flush()
                 main.wait_stream(side)

@@ -672,6 +672,11 @@ class Optimizer:
         state["allreduce"] = None
         return state
 
+    def reduce(self, params):
+        """data parallel: average the gradients of the groups of `params` now, on the current stream (no-op on one GPU)"""
+        if self.allreduce is not None:
+            self.store.reduce(self.store.groups_of(list(params)), self.allreduce)
+
     def apply(self, loss, params, active=None):
         """grad-norm / clip / weight decay / Adam on the groups of `params` (the backward has already run).  `active` restricts the
         norm / clip / Adam part to the groups of those parameters; the other groups of `params` only get the weight decay."""

@@ -16,17 +16,19 @@ class DataParallel:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.nccl = dist.get_backend(group) == "nccl"
         self.n_allreduce = 0
         self.bytes_allreduced = 0
 
     def allreduce(self, flats):
-        """average flat fp32 gradient buffers in place: one collective per optimizer-group buffer"""
+        """average flat fp32 gradient buffers in place: one collective per optimizer-group buffer, issued on the CURRENT stream (the
+        agent calls this on the stream whose backward produced the gradients, so that a finished group's collective runs beside the
+        other stream's remaining backward)"""
         if self.world == 1:
             return
-        avg = getattr(dist.ReduceOp, "AVG", None)
         for g in flats:
-            if avg is not None and g.is_cuda:
-                dist.all_reduce(g, op=avg, group=self.group)
+            if self.nccl and g.is_cuda:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
                 g.div_(self.world)
@@ -37,6 +39,10 @@ class DataParallel:
         """concatenate a 1-D tensor from every rank (equal lengths)"""
         if self.world == 1:
             return flat
+        if not self.nccl and flat.is_cuda:          # gloo has no CUDA all-gather: stage through the host (tests on a single GPU)
+            parts = [torch.empty(flat.numel(), dtype=flat.dtype) for _ in range(self.world)]
+            dist.all_gather(parts, flat.detach().cpu().contiguous(), group=self.group)
+            return torch.cat(parts).to(flat.device)
         out = torch.empty(self.world * flat.numel(), device=flat.device, dtype=flat.dtype)
         dist.all_gather_into_tensor(out, flat.contiguous(), group=self.group)
         return out

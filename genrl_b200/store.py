@@ -32,6 +32,7 @@ class ParamGroup:
         self.name = name
         self.params = [p for p in params]
         self.touched = False
+        self.reduced = False               # gradients already averaged over the data-parallel group (reduce() ran early)
         self.trainable = trainable
         self.compute_dtype = compute_dtype
         offs, total = [], 0
@@ -131,6 +132,17 @@ class ParamStore:
                 out.append(g)
         return out
 
+    def reduce(self, groups, allreduce):
+        """average the gradients of `groups` over the data-parallel ranks NOW, on the current stream (called right after the backward
+        that produced them, so the collective overlaps whatever the other stream is still computing); step() then skips them"""
+        if allreduce is None:
+            return
+        todo = [g for g in groups if g.trainable and g.touched and not g.reduced]
+        if todo:
+            allreduce([g.grad for g in todo])
+            for g in todo:
+                g.reduced = True
+
     def refresh_all(self):
         for g in self.groups.values():
             g.refresh()
@@ -141,8 +153,12 @@ class ParamStore:
         Returns the device scalar holding the (pre-clip) gradient norm."""
         st = ops._st()
         active = [g for g in groups if g.trainable and g.touched and (only is None or any(g is o for o in only))]
-        if allreduce is not None and active:
-            allreduce([g.grad for g in active])
+        if allreduce is not None:
+            pending = [g for g in active if not g.reduced]
+            if pending:
+                allreduce([g.grad for g in pending])
+        for g in active:
+            g.reduced = False
         first = True
         for g in active:
             lib.genrl_grad_sumsq(st, g.grad.data_ptr(), g.numel, self.sumsq.data_ptr(), int(first))
