@@ -34,6 +34,10 @@ CASES = {
                                       "actor_ent": 3e-4}),
     # BASELINE configs[3] flavour: 9 actions and an extra low-dimensional `state` observation key that the GenRL encoder/decoder ignore
     # (conf/env/dmc_pixels.yaml mlp_keys '$^'); single sequence (B = 1) as the ragged edge
+    # conf/defaults/dreamer_v3.yaml:5 — single_obs_posterior: false: the posterior reads [deter | embed], so nothing can be hoisted out of
+    # the time loop and observe() runs step by step (EnsembleRSSM._observe_stepwise); resets included
+    "tiny_dreamer_v3": dict(B=3, T=8, H=4, A=4, clip=32, resets=0.2, kind="dreamer",
+                            over=(lambda o: {**o, "rssm": {**o["rssm"], "single_obs_posterior": False}})(tiny_overrides(units=32, stoch=4, discrete=8))),
     "tiny_kitchen": dict(B=1, T=16, H=4, A=9, clip=32, resets=0.2, kind="genrl", over=tiny_overrides(), extra_obs={"state": 30}, slim=True),
 }
 

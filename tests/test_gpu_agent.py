@@ -41,7 +41,7 @@ def relclose(a, b, rtol, atol, msg):
     assert err <= atol + rtol * scale, f"{msg}: max abs err {err:.3e} (scale {scale:.3e})"
 
 
-@pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer"])
+@pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer", "tiny_dreamer_v3"])
 def test_agent_update_matches_reference_golden_fp32(case):
     from genrl_b200 import ops
     agent, data, g, meta = build_agent(case, 32)

@@ -8,7 +8,7 @@ from oracle import genrl_oracle as O
 from tests.golden_utils import load_case
 
 
-@pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer"])
+@pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer", "tiny_dreamer_v3"])
 def test_oracle_matches_reference_golden(case):
     torch.set_num_threads(1)
     g, meta, cfg = load_case(case)
