@@ -298,12 +298,34 @@ def run_native(args):
     ms_e2e = timed(e2e_step, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    # the same public call fed by the on-GPU replay store: per step the host samples B (episode, offset) pairs with the
+    # reference's numpy calls, uploads B int64 start rows from pinned memory, one gather kernel per key builds the batch in HBM
+    import numpy as np
+    from genrl_b200.replay import ReplayBuffer, make_replay_loader
+    ep_len, n_eps = 4 * args.length, 24
+    rbuf = ReplayBuffer(length=args.length, capacity=n_eps * ep_len, device=dev, max_episode_steps=ep_len)
+    for e in range(n_eps):
+        epi = {k: v[0].numpy() for k, v in synthetic(1, ep_len, args.action_dim, 1000 + 97 * rank + e).items()}
+        rbuf.store_episode(episode=epi, run_checks=False)
+    np.random.seed(7 + rank)
+    riter = iter(make_replay_loader(rbuf, args.batch))
+
+    def replay_step(i):
+        m = step(next(riter), i)
+        float(m["model_loss"])
+    for i in range(2):
+        replay_step(i)
+    ms_replay = timed(replay_step, args.steps)
+
     frames = world * args.batch * args.length
     line = {"metric": "seq_frames_per_s_full_genrl_update", "value": frames / (ms_step * 1e-3), "unit": "seq-frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == 16 else "f32", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "seq-frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h_bytes, "pipeline": "pinned host batch i+1 copied on a second stream while step i runs; loss of every step read back"},
+            "e2e_replay": {"value": frames / (ms_replay * 1e-3), "unit": "seq-frames/s", "ms_per_step": ms_replay, "h2d_bytes_per_step": 8 * args.batch,
+                           "d2h_bytes_per_step": d2h_bytes, "pipeline": "batch gathered in HBM from the on-GPU episode store (genrl_b200.replay) behind "
+                           "next(replay_iter); host samples the windows with the reference's numpy calls; loss of every step read back"},
             "gpu_launches": int(launches), "clocks": clk}
 
     if rank == 0 and world == 1 and not args.no_roofline:

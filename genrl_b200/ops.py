@@ -731,6 +731,37 @@ def lambda_return(reward, value, gamma, lam):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# video-text reward (max-cosine score with sliding-window alignment)
+# ---------------------------------------------------------------------------------------------------------------
+class _VlmReward(Function):
+    """reward[t,n] = maxcos(pa[t,n], pt[max(t - b_n, 0), n]), b_n = best alignment offset (tools/genrl_utils.py:250-277, :344-366)."""
+
+    @staticmethod
+    def forward(ctx, pa, pt, n_frames, align):
+        T, N, E = pa.shape
+        pa, pt = pa.contiguous(), pt.contiguous().to(pa.dtype)
+        reward = torch.empty(T, N, device=pa.device, dtype=torch.float32)
+        shift = torch.empty(N, device=pa.device, dtype=torch.int32)
+        lib.genrl_vlm_reward_fwd(_st(), _p(pa), _p(pt), _p(reward), _p(shift), T, N, E, int(n_frames), int(bool(align)), _CODE[pa.dtype])
+        ctx.save_for_backward(pa, pt, shift)
+        ctx.mark_non_differentiable(shift)
+        return reward, shift
+
+    @staticmethod
+    def backward(ctx, dreward, _dshift):
+        pa, pt, shift = ctx.saved_tensors
+        T, N, E = pa.shape
+        dpa = torch.empty_like(pa)
+        lib.genrl_vlm_reward_bwd(_st(), _p(pa), _p(pt), _p(shift), _p(dreward.contiguous().float()), _p(dpa), T, N, E, _CODE[pa.dtype])
+        return dpa, None, None, None
+
+
+def vlm_reward(pa, pt, n_frames=8, align=True):
+    """pa, pt: [T, N, E] projections (compute dtype) -> (reward fp32 [T, N], shift int32 [N])"""
+    return _VlmReward.apply(pa, pt, n_frames, align)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # conv stacks
 # ---------------------------------------------------------------------------------------------------------------
 

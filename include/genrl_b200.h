@@ -90,6 +90,18 @@ int genrl_lambda_return_fwd(void* stream, const float* reward, const float* valu
 int genrl_lambda_return_bwd(void* stream, const float* dtarget, const float* dt_scale, float gamma, float lambda, float* dreward,
                             float* dvalue, int H, long long N);
 
+/* Replay window gather (tools/replay.py:223-236): batch[b] = store[start[b] : start[b] + L] for B windows of L rows of row_bytes each; store and
+ * batch are device buffers, start is a device array of B first-row indices into the flat episode store of one key. */
+int genrl_replay_gather(void* stream, const void* store, const long long* start, long long row_bytes, int B, int L, void* batch);
+
+/* Video-text reward of the imagination behaviour: tools/genrl_utils.py:240-243 (max_cosine), :250-277 (compute_reward), :344-366
+ * (align_sequence: best of T - n_frames window offsets, target delayed by that offset).  pa / pt: decoder-input projections of the imagined and
+ * of the cached target latents, [T, N, E] time-major in `dtype`; reward fp32 [T, N]; shift int [N] (the chosen offset, kept for the backward). */
+int genrl_vlm_reward_fwd(void* stream, const void* pa, const void* pt, float* reward, int* shift, int T, long long N, int E, int n_frames,
+                         int align, int dtype);
+int genrl_vlm_reward_bwd(void* stream, const void* pa, const void* pt, const int* shift, const float* dreward, void* dpa, int T, long long N,
+                         int E, int dtype);
+
 /* MSEDist.log_prob against uint8 observations with the /255-0.5 preprocessing fused: dreamer_utils.py:74-83, dreamer.py:294-295. */
 int genrl_mse_fwd(void* stream, const float* mean, const unsigned char* obs, float* like, long long rows, int E);
 int genrl_mse_bwd(void* stream, const float* mean, const unsigned char* obs, const float* dlike, const float* gscale, float scale,

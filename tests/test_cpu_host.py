@@ -142,7 +142,7 @@ def test_bench_roofline_pass_is_single_gpu_only():
     """the roofline pass re-runs eager steps on rank 0 only; under data parallelism those steps contain NCCL collectives the other
     ranks never join (it deadlocked an 8-GPU run) — it must be gated on world == 1, like the CPU baseline"""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    call = src.index("roofline_pass(step, devb, nb, lib, args, agent)")
+    call = src.index("roofline_pass(step, devb, nb, lib, args, agent, ms_step)")
     guard = src.rfind("\n    if ", 0, call)
     assert "world == 1" in src[guard:call], src[guard:call]
     cb = src.index('line["cpu_baseline"] = cpu_baseline(args, agent)')

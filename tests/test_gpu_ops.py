@@ -512,3 +512,38 @@ def test_thin_convT3_mse_fused(dtype):
         close(xd.grad.reshape(N, Hi, Hi, C).permute(0, 3, 1, 2), xr.grad, msg="convT3 dx", **tol)
         close(cd.weight.grad, wr.grad, msg="convT3 dW", **tol)
         close(cd.bias.grad, br.grad, msg="convT3 db", **tol)
+
+
+@pytest.mark.parametrize("dtype,T,N,E,align", [(torch.float32, 11, 37, 96, True), (torch.float32, 16, 64, 1536, True),
+                                               (torch.bfloat16, 16, 50, 1536, True), (torch.float32, 5, 9, 64, False)])
+def test_vlm_reward_alignment_and_gradient(dtype, T, N, E, align):
+    """fused video-text reward (tools/genrl_utils.py:240-243, :250-277, :344-366) vs the oracle's max_cosine + window alignment on the same
+    projections: chosen offsets bit-equal, rewards and d reward / d projection within the mode's tolerance"""
+    g = torch.Generator().manual_seed(3)
+    pa = torch.randn(T, N, E, generator=g) * (0.5 + torch.rand(T, N, 1, generator=g))
+    pt = torch.randn(T, N, E, generator=g)
+    # make a clear best offset for some rows: the imagined sequence repeats the target's head with a delay
+    for n in range(0, N, 3):
+        d = n % max(T - 8, 1) if align else 0
+        pa[d:d + min(8, T - d), n] = pt[:min(8, T - d), n] * 1.3 + 0.05 * torch.randn(min(8, T - d), E, generator=g)
+    q = lambda x: x.to(dtype).float()
+    pa_r = q(pa).clone().requires_grad_(True)
+    F_ = 8
+    if align:
+        win = torch.stack([O.max_cosine(q(pt)[:F_], pa_r[t:t + F_]).mean(0) for t in range(T - F_)], 0)
+        b = win.argmax(0)
+    else:
+        b = torch.zeros(N, dtype=torch.long)
+    idx = (torch.arange(T)[:, None] - b[None]).clamp(min=0)
+    shifted = torch.gather(q(pt), 0, idx[:, :, None].expand(T, N, E))
+    ref = O.max_cosine(shifted, pa_r)
+    w = torch.randn(T, N, generator=g)
+    (ref * w).sum().backward()
+    pa_d = pa.to(DEV, dtype).requires_grad_(True)
+    reward, shift = ops.vlm_reward(pa_d, pt.to(DEV, dtype), F_, align)
+    (reward * w.to(DEV)).sum().backward()
+    assert torch.equal(shift.cpu().long(), b)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert (reward.cpu() - ref.detach()).abs().max() <= tol
+    gscale = float(pa_r.grad.abs().max())
+    assert (pa_d.grad.float().cpu() - pa_r.grad).abs().max() <= tol * gscale + (1e-6 if dtype == torch.float32 else 1e-2 * gscale)

@@ -267,3 +267,24 @@ def test_sharded_gradients_average_to_the_global_batch_gradient():
         for k, v in ref[name].items():
             s = float(v.abs().max()) + 1e-12
             torch.testing.assert_close(acc[name][k] / s, v / s, rtol=0, atol=2e-5, msg=lambda m: f"{name} {k}: {m}")
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_replay_oracle_reproduces_the_reference_batches(ci):
+    """oracle/replay_oracle.py (tools/replay.py:175-236 restated) against the sha256 of the batches the unmodified
+    reference ReplayBuffer yielded for the same episodes and numpy seeds (oracle/make_golden_replay.py)"""
+    import json, os
+    from tests.golden_utils import GOLDEN
+    from oracle.replay_oracle import ReplayOracle
+    from oracle.make_golden_replay import script, batch_digest, L, B
+    case = json.load(open(os.path.join(GOLDEN, "replay_small.json")))["cases"][ci]
+    ora = ReplayOracle(L, case["capacity"], case["min_t"])
+    n = 0
+    for op, arg in script(case):
+        if op == "store":
+            ora.store_episode(arg)
+        else:
+            np.random.seed(arg)
+            assert batch_digest(ora.sample(B)) == case["digests"][n], n
+            n += 1
+    assert n == len(case["digests"]) and n > 20
