@@ -103,4 +103,32 @@ __device__ __forceinline__ float u32_to_unit_open(uint32_t x) {   // (0,1]
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------------
+// One update is ~1 600 launches of mostly 4-20 us kernels replayed from a CUDA graph: the drain -> launch -> ramp bubble between two
+// dependent kernels is a sizeable share of the step.  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and calls pdl_sync() before its first access to global memory:
+//   griddepcontrol.wait               blocks until the preceding grid has completed and its memory operations are visible
+//   griddepcontrol.launch_dependents  lets the NEXT grid's CTAs become resident (they park in their own wait)
+// so a kernel's launch latency, CTA scheduling and (for the tcgen05 kernels) barrier init / TMEM allocation / descriptor prefetch
+// overlap the tail of its predecessor.  The trigger comes after the wait, so at most one successor is parked at any time.
+// A predecessor that is not ours (an ATen kernel) never triggers early: the wait then returns at once, ordinary stream semantics.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();      // GENRL_PDL=0 turns the launch attribute off (runtime.cu)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "kernel argument count");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace genrl

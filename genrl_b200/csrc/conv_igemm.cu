@@ -182,6 +182,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  genrl::pdl_sync();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA: filter k-blocks ------------------------------
@@ -375,6 +376,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  genrl::pdl_sync();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -492,6 +494,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmS, const ConvWgParams p)
 // W4 is [A][B][k][k] fp32: Conv2d weight [Cout][Cin] (A = Cout, used by its dgrad) or ConvTranspose2d weight [Cin][Cout] (A = Cin, forward)
 __global__ void __launch_bounds__(256) conv_pack_parity_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int A, int B, int k, int T,
                                                                int Cpad) {
+  genrl::pdl_sync();
   const long long K = (long long)T * T * A;
   const long long total = 4LL * Cpad * K;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -508,6 +511,7 @@ __global__ void __launch_bounds__(256) conv_pack_parity_kernel(const float* __re
 
 // gather form with channel padding: Wg[a, (ky*k + kx)*Cp + b] = W4[a][b][ky][kx]  (0 for b >= B)
 __global__ void __launch_bounds__(256) conv_pack_gather_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int A, int B, int k, int Cp) {
+  genrl::pdl_sync();
   const long long total = (long long)A * k * k * Cp;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int b = (int)(i % Cp);
@@ -520,6 +524,7 @@ __global__ void __launch_bounds__(256) conv_pack_gather_kernel(const float* __re
 // grad[a][b][tap] += dwp[a, tap*Cp + b]
 __global__ void __launch_bounds__(256) conv_unpack_wgrad_kernel(const float* __restrict__ dwp, long long ld, float* __restrict__ grad, int A, int B, int kk,
                                                                 int Cp) {
+  genrl::pdl_sync();
   const long long total = (long long)A * B * kk;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int tap = (int)(i % kk);
@@ -532,6 +537,7 @@ __global__ void __launch_bounds__(256) conv_unpack_wgrad_kernel(const float* __r
 // NCHW fp32 [N,C,H,W] -> NHWC bf16 with the channel dimension zero-padded to Cp
 __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long N, int C, int H, int W,
                                                                int Cp) {
+  genrl::pdl_sync();
   const long long total = N * H * W;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long n = i / ((long long)H * W);
@@ -543,6 +549,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_pad_kernel(const float* __re
 // uint8 NCHW observation -> (x/255 - 0.5) bf16 NHWC with the channel dimension zero-padded to 8 (one 16-byte store per pixel):
 // the encoder's first layer then runs on the implicit-GEMM path like every other layer (preprocess dreamer.py:294-295 fused here)
 __global__ void __launch_bounds__(256) u8_nchw_to_nhwc8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ y, long long N, int C, int HW) {
+  genrl::pdl_sync();
   const long long total = N * HW;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long n = i / HW;
@@ -585,7 +592,7 @@ static int launch_fwd(const CUtensorMap& tw, const ConvFwdParams& p, cudaStream_
   }
   const long long tiles = ((p.g.rows + CV_BM - 1) / CV_BM) * ceil_div(p.N, BN);
   dim3 grid((unsigned)std::min<long long>(tiles, (long long)sms * ctas_per_sm), 1, 1);
-  kern<<<grid, CVF_THREADS, SMEM, st>>>(tw, p);
+  genrl::launch_pdl(kern, grid, CVF_THREADS, SMEM, st, tw, p);
   return check_launch("conv_fwd_kernel");
 }
 
@@ -675,35 +682,35 @@ extern "C" int genrl_conv_igemm_wgrad(void* stream, const void* in, int Nimg, in
     attr_set = true;
   }
   dim3 grid(ceil_div(p.g.K, BN), ceil_div(Cs, CV_BM), splits);
-  kern<<<grid, CV_THREADS, SMEM, st>>>(tm, p);
+  genrl::launch_pdl(kern, grid, CV_THREADS, SMEM, st, tm, p);
   return check_launch("conv_wgrad_kernel");
 }
 
 extern "C" int genrl_conv_pack_parity(void* stream, const float* w, void* dst, int A, int B, int k, int Cpad) {
   const int T = (k + 1) / 2;
   const long long total = 4LL * Cpad * T * T * A;
-  conv_pack_parity_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  genrl::launch_pdl(conv_pack_parity_kernel, (int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       w, reinterpret_cast<__nv_bfloat16*>(dst), A, B, k, T, Cpad);
   return check_launch("conv_pack_parity");
 }
 
 extern "C" int genrl_conv_pack_gather(void* stream, const float* w, void* dst, int A, int B, int k, int Cp) {
   const long long total = (long long)A * k * k * Cp;
-  conv_pack_gather_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  genrl::launch_pdl(conv_pack_gather_kernel, (int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       w, reinterpret_cast<__nv_bfloat16*>(dst), A, B, k, Cp);
   return check_launch("conv_pack_gather");
 }
 
 extern "C" int genrl_conv_unpack_wgrad(void* stream, const float* dwp, long long ld, float* grad, int A, int B, int k, int Cp) {
   const long long total = (long long)A * B * k * k;
-  conv_unpack_wgrad_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dwp, ld, grad, A, B,
+  genrl::launch_pdl(conv_unpack_wgrad_kernel, (int)std::min<long long>((total + 255) / 256, 148 * 8), 256, 0, reinterpret_cast<cudaStream_t>(stream), dwp, ld, grad, A, B,
                                                                                                                                 k * k, Cp);
   return check_launch("conv_unpack_wgrad");
 }
 
 extern "C" int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, long long N, int C, int H, int W, int Cp) {
   const long long total = N * H * W;
-  nchw_to_nhwc_pad_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  genrl::launch_pdl(nchw_to_nhwc_pad_kernel, (int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(y), N, C, H, W, Cp);
   return check_launch("nchw_to_nhwc_pad");
 }
@@ -711,7 +718,7 @@ extern "C" int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, lon
 extern "C" int genrl_u8_nchw_to_nhwc8(void* stream, const void* x, void* y, long long N, int C, int H, int W) {
   GENRL_REQUIRE(C <= 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "u8_nchw_to_nhwc8: at most 8 channels, 16-byte aligned output");
   const long long total = N * H * W;
-  u8_nchw_to_nhwc8_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  genrl::launch_pdl(u8_nchw_to_nhwc8_kernel, (int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint8_t*>(x), reinterpret_cast<uint4*>(y), N, C, H * W);
   return check_launch("u8_nchw_to_nhwc8");
 }

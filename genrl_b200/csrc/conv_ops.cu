@@ -14,6 +14,7 @@ namespace genrl {
 template <typename TI, typename TO, bool U8_NCHW>
 __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, TO* __restrict__ col, long long ldcol, int N, int H, int W, int C,
                                                      int k, int Ho, int Wo) {
+  genrl::pdl_sync();
   const long long total = (long long)N * Ho * Wo * k * k * C;
   const int Kc = k * k * C;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const TI* __restrict__ x, T
 template <typename TI, typename TO, bool NCHW_OUT>
 __global__ void __launch_bounds__(256) col2im_kernel(const TI* __restrict__ col, long long ldcol, const float* __restrict__ bias, TO* __restrict__ y,
                                                      int N, int Hi, int Wi, int C, int k, int Ho, int Wo) {
+  genrl::pdl_sync();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     int c, ow, oh; long long n;
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const TI* __restrict__ col,
 // NCHW fp32 [N,C,H,W] -> NHWC T  (gradient of the final decoder layer arrives as NCHW)
 template <typename TO>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, TO* __restrict__ y, int N, int C, int H, int W) {
+  genrl::pdl_sync();
   const long long total = (long long)N * C * H * W;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     int c = (int)(i % C); int w = (int)((i / C) % W); int h = (int)((i / ((long long)C * W)) % H); long long n = i / ((long long)C * W * H);
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 // generic [A, B, P] <-> [A, P, B] permutation with cast; forward (pack) overwrites, backward (unpack) accumulates into fp32
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) permute_abp_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long A, int B, int P, int accumulate) {
+  genrl::pdl_sync();
   // src is [A, B, P]; dst is [A, P, B]
   const long long total = A * B * P;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__(256) permute_abp_kernel(const TI* __restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_vec_kernel(const T* __restrict__ x, T* __restrict__ col, long long ldcol, int N, int H, int W, int C,
                                                          int k, int Ho, int Wo) {
+  genrl::pdl_sync();
   const int seg8 = k * C / 8;
   const long long total = (long long)N * Ho * Wo * k * seg8;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -99,6 +104,7 @@ __global__ void __launch_bounds__(256) im2col_vec_kernel(const T* __restrict__ x
 template <typename TI, typename TO, bool U8_NCHW>
 __global__ void __launch_bounds__(256) im2col_seg_kernel(const TI* __restrict__ x, TO* __restrict__ col, long long ldcol, int N, int H, int W, int C,
                                                          int k, int Ho, int Wo) {
+  genrl::pdl_sync();
   const long long total = (long long)N * Ho * Wo * k;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int kh = (int)(i % k);
@@ -122,6 +128,7 @@ __global__ void __launch_bounds__(256) im2col_seg_kernel(const TI* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(256) col2im_vec_kernel(const T* __restrict__ col, long long ldcol, const float* __restrict__ bias, T* __restrict__ y,
                                                          int N, int Hi, int Wi, int C, int k, int Ho, int Wo) {
+  genrl::pdl_sync();
   const int C8 = C / 8;
   const long long total = (long long)N * Ho * Wo * C8;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -168,18 +175,18 @@ extern "C" int genrl_im2col(void* stream, const void* x, int x_dtype, void* col,
   cudaStream_t st = ST(stream);
   const long long segs = (long long)N * Ho * Wo * k;
   if (x_dtype == -1) {
-    if (col_dtype == GENRL_F32) im2col_seg_kernel<uint8_t, float, true><<<grid_for(segs), 256, 0, st>>>((const uint8_t*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
-    else im2col_seg_kernel<uint8_t, __nv_bfloat16, true><<<grid_for(segs), 256, 0, st>>>((const uint8_t*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    if (col_dtype == GENRL_F32) genrl::launch_pdl(im2col_seg_kernel<uint8_t, float, true>, grid_for(segs), 256, 0, st, (const uint8_t*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+    else genrl::launch_pdl(im2col_seg_kernel<uint8_t, __nv_bfloat16, true>, grid_for(segs), 256, 0, st, (const uint8_t*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
   } else {
     GENRL_REQUIRE(x_dtype == col_dtype, "im2col: dtype mismatch");
     if (col_dtype == GENRL_F32) {
       if (C % 8 == 0 && vec_ok<float>(x, C) && vec_ok<float>(col, ldcol))
-        im2col_vec_kernel<float><<<grid_for(total / 8), 256, 0, st>>>((const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
-      else im2col_seg_kernel<float, float, false><<<grid_for(segs), 256, 0, st>>>((const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+        genrl::launch_pdl(im2col_vec_kernel<float>, grid_for(total / 8), 256, 0, st, (const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
+      else genrl::launch_pdl(im2col_seg_kernel<float, float, false>, grid_for(segs), 256, 0, st, (const float*)x, (float*)col, ldcol, N, H, W, C, k, Ho, Wo);
     } else {
       if (C % 8 == 0 && vec_ok<__nv_bfloat16>(x, C) && vec_ok<__nv_bfloat16>(col, ldcol))
-        im2col_vec_kernel<__nv_bfloat16><<<grid_for(total / 8), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
-      else im2col_seg_kernel<__nv_bfloat16, __nv_bfloat16, false><<<grid_for(segs), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+        genrl::launch_pdl(im2col_vec_kernel<__nv_bfloat16>, grid_for(total / 8), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
+      else genrl::launch_pdl(im2col_seg_kernel<__nv_bfloat16, __nv_bfloat16, false>, grid_for(segs), 256, 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, ldcol, N, H, W, C, k, Ho, Wo);
     }
   }
   return check_launch("im2col");
@@ -194,19 +201,19 @@ extern "C" int genrl_col2im(void* stream, const void* col, long long ldcol, int 
   cudaStream_t st = ST(stream);
   if (nchw_out) {
     GENRL_REQUIRE(y_dtype == GENRL_F32, "col2im: NCHW output is fp32");
-    if (col_dtype == GENRL_F32) col2im_kernel<float, float, true><<<g, 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
-    else col2im_kernel<__nv_bfloat16, float, true><<<g, 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+    if (col_dtype == GENRL_F32) genrl::launch_pdl(col2im_kernel<float, float, true>, g, 256, 0, st, (const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+    else genrl::launch_pdl(col2im_kernel<__nv_bfloat16, float, true>, g, 256, 0, st, (const __nv_bfloat16*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
   } else {
     GENRL_REQUIRE(y_dtype == col_dtype, "col2im: dtype mismatch");
     const bool bias_ok = bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
     if (col_dtype == GENRL_F32) {
       if (C % 8 == 0 && bias_ok && vec_ok<float>(col, ldcol) && vec_ok<float>(y, C))
-        col2im_vec_kernel<float><<<grid_for(total / 8), 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
-      else col2im_kernel<float, float, false><<<g, 256, 0, st>>>((const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+        genrl::launch_pdl(col2im_vec_kernel<float>, grid_for(total / 8), 256, 0, st, (const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
+      else genrl::launch_pdl(col2im_kernel<float, float, false>, g, 256, 0, st, (const float*)col, ldcol, bias, (float*)y, N, Hi, Wi, C, k, Ho, Wo);
     } else {
       if (C % 8 == 0 && bias_ok && vec_ok<__nv_bfloat16>(col, ldcol) && vec_ok<__nv_bfloat16>(y, C))
-        col2im_vec_kernel<__nv_bfloat16><<<grid_for(total / 8), 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
-      else col2im_kernel<__nv_bfloat16, __nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
+        genrl::launch_pdl(col2im_vec_kernel<__nv_bfloat16>, grid_for(total / 8), 256, 0, st, (const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
+      else genrl::launch_pdl(col2im_kernel<__nv_bfloat16, __nv_bfloat16, false>, g, 256, 0, st, (const __nv_bfloat16*)col, ldcol, bias, (__nv_bfloat16*)y, N, Hi, Wi, C, k, Ho, Wo);
     }
   }
   return check_launch("col2im");
@@ -215,8 +222,8 @@ extern "C" int genrl_col2im(void* stream, const void* col, long long ldcol, int 
 extern "C" int genrl_nchw_to_nhwc(void* stream, const float* x, void* y, int y_dtype, int N, int C, int H, int W) {
   const long long total = (long long)N * C * H * W;
   if (total <= 0) return 0;
-  if (y_dtype == GENRL_F32) nchw_to_nhwc_kernel<float><<<grid_for(total), 256, 0, ST(stream)>>>(x, (float*)y, N, C, H, W);
-  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, ST(stream)>>>(x, (__nv_bfloat16*)y, N, C, H, W);
+  if (y_dtype == GENRL_F32) genrl::launch_pdl(nchw_to_nhwc_kernel<float>, grid_for(total), 256, 0, ST(stream), x, (float*)y, N, C, H, W);
+  else genrl::launch_pdl(nchw_to_nhwc_kernel<__nv_bfloat16>, grid_for(total), 256, 0, ST(stream), x, (__nv_bfloat16*)y, N, C, H, W);
   return check_launch("nchw_to_nhwc");
 }
 
@@ -226,9 +233,9 @@ extern "C" int genrl_permute_abp(void* stream, const void* src, int src_dtype, v
   if (total <= 0) return 0;
   unsigned g = grid_for(total);
   cudaStream_t st = ST(stream);
-  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) permute_abp_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, A, B, P, accumulate);
-  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) permute_abp_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, A, B, P, accumulate);
-  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) permute_abp_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, A, B, P, accumulate);
-  else permute_abp_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, A, B, P, accumulate);
+  if (src_dtype == GENRL_F32 && dst_dtype == GENRL_F32) genrl::launch_pdl(permute_abp_kernel<float, float>, g, 256, 0, st, (const float*)src, (float*)dst, A, B, P, accumulate);
+  else if (src_dtype == GENRL_F32 && dst_dtype == GENRL_BF16) genrl::launch_pdl(permute_abp_kernel<float, __nv_bfloat16>, g, 256, 0, st, (const float*)src, (__nv_bfloat16*)dst, A, B, P, accumulate);
+  else if (src_dtype == GENRL_BF16 && dst_dtype == GENRL_F32) genrl::launch_pdl(permute_abp_kernel<__nv_bfloat16, float>, g, 256, 0, st, (const __nv_bfloat16*)src, (float*)dst, A, B, P, accumulate);
+  else genrl::launch_pdl(permute_abp_kernel<__nv_bfloat16, __nv_bfloat16>, g, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, A, B, P, accumulate);
   return check_launch("permute_abp");
 }

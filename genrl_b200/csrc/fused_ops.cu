@@ -31,6 +31,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS) ln_act_fwd_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int act, T* __restrict__ y,
                                                              long long ldy, float* __restrict__ stats, long long M, int D) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
     const T* xr = x + row * ldx;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(THREADS) ln_act_bwd_kernel(const T* __restrict
                                                              const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlin_bias,
                                                              long long M, int D) {
+  genrl::pdl_sync();
   extern __shared__ float sm[];        // [3][D] column partials
   float* s_dg = sm; float* s_db = sm + D; float* s_dl = sm + 2 * D;
   const bool need_cols = dgamma != nullptr || dlin_bias != nullptr;
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(THREADS) ln_act_bwd_kernel(const T* __restrict
 // column sum: out[c] += sum_rows x[r,c]   (bias gradients of Linear layers not followed by LN)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, long long M, int D, long long rows_per_block) {
+  genrl::pdl_sync();
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   for (int c = blockIdx.x * 256 + threadIdx.x; c < D; c += gridDim.x * 256) {
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(THREADS) gru_fwd_kernel(const T* __restrict__ 
                                                           const float* __restrict__ beta, const float* __restrict__ hprev, long long ldh,
                                                           float* __restrict__ hout, long long ldho, T* __restrict__ hout_t, long long ldht,
                                                           float* __restrict__ stats, long long M, int D) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int D3 = 3 * D;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * WARPS) {
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(THREADS) gru_bwd_kernel(const float* __restric
                                                           const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
                                                           T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int D) {
+  genrl::pdl_sync();
   extern __shared__ float sm[];        // [2][3D]
   const int D3 = 3 * D;
   float* s_dg = sm; float* s_db = sm + D3;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(THREADS) cat_sample_fwd_kernel(const float* __
                                                                  const unsigned long long* __restrict__ step_dev, int sample,
                                                                  T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
                                                                  long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S, int K) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long total = rows * S;
   if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;     // fresh stream every optimisation step (CUDA-graph safe)
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(THREADS) cat_sample_fwd_kernel(const float* __
 template <typename T>
 __global__ void __launch_bounds__(THREADS) cat_sample_bwd_kernel(const float* __restrict__ logit, const T* __restrict__ dstoch, long long ld_ds,
                                                                  int sample, float* __restrict__ dlogit, int accumulate, long long rows, int S, int K) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long total = rows * S;
   for (long long g = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); g < total; g += (long long)gridDim.x * WARPS) {
@@ -358,6 +365,7 @@ __global__ void __launch_bounds__(128) cat_sample_fwd_thr_kernel(const float* __
                                                                  const unsigned long long* __restrict__ step_dev, int sample,
                                                                  T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
                                                                  long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S) {
+  genrl::pdl_sync();
   const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
   if (g >= rows * S) return;
   if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;
@@ -403,6 +411,7 @@ __global__ void __launch_bounds__(128) cat_sample_fwd_thr_kernel(const float* __
 template <typename T>
 __global__ void __launch_bounds__(128) cat_sample_bwd_thr_kernel(const float* __restrict__ logit, const T* __restrict__ dstoch, long long ld_ds,
                                                                  int sample, float* __restrict__ dlogit, int accumulate, long long rows, int S) {
+  genrl::pdl_sync();
   const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
   if (g >= rows * S) return;
   float p[CK], pi[CK], usum, dpi[CK], dl[CK];
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(128) cat_sample_bwd_thr_kernel(const float* __
 // S == 32, K == 32: one warp per row, one latent per lane
 __global__ void __launch_bounds__(128) kl_fwd_thr_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, float free_bits,
                                                          float* __restrict__ value, float* __restrict__ out, long long rows) {
+  genrl::pdl_sync();
   const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
   const long long row = g >> 5;
   float kl = 0.f, el = 0.f, er = 0.f;
@@ -446,6 +456,7 @@ __global__ void __launch_bounds__(128) kl_fwd_thr_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) kl_bwd_thr_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, const float* __restrict__ value,
                                                          float free_bits, float w_lhs, float w_rhs, const float* __restrict__ gscale,
                                                          float* __restrict__ dlhs, float* __restrict__ drhs, long long rows) {
+  genrl::pdl_sync();
   const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
   const long long row = g >> 5;
   if (row >= rows) return;
@@ -478,6 +489,7 @@ __global__ void __launch_bounds__(128) kl_bwd_thr_kernel(const float* __restrict
 // =================================================================================================
 __global__ void __launch_bounds__(THREADS) kl_fwd_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, float free_bits,
                                                          float* __restrict__ value, float* __restrict__ out, long long rows, int S, int K) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   float acc_loss = 0.f, acc_val = 0.f, acc_el = 0.f, acc_er = 0.f;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
@@ -508,6 +520,7 @@ __global__ void __launch_bounds__(THREADS) kl_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(THREADS) kl_bwd_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, const float* __restrict__ value,
                                                          float free_bits, float w_lhs, float w_rhs, const float* __restrict__ gscale,
                                                          float* __restrict__ dlhs, float* __restrict__ drhs, long long rows, int S, int K) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const float gs = gscale ? *gscale : 1.0f;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
@@ -551,6 +564,7 @@ __device__ __forceinline__ float symexpf_(float y) { return copysignf(expf(fabsf
 // mode 0: out[r] = log_prob(x[r]) ; mode 1: out[r] = mean
 __global__ void __launch_bounds__(THREADS) twohot_fwd_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, int mode,
                                                              float* __restrict__ out, long long rows) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
     const float* lg = logits + row * ldl;
@@ -596,6 +610,7 @@ __global__ void __launch_bounds__(THREADS) twohot_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(THREADS) twohot_bwd_kernel(const float* __restrict__ logits, long long ldl, const float* __restrict__ x, int mode,
                                                              const float* __restrict__ dout, float scale, float* __restrict__ dlogits, long long lddl,
                                                              long long rows) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   for (long long row = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * WARPS) {
     const float* lg = logits + row * ldl;
@@ -645,6 +660,7 @@ template <typename T>
 __global__ void actor_head_fwd_kernel(const float* __restrict__ out, long long ldo, const float* __restrict__ eps, int use_mean,
                                       float* __restrict__ action, long long lda, T* __restrict__ action_t, long long ldat,
                                       float* __restrict__ ent, long long rows, int A) {
+  genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   float e = 0.f;
@@ -663,6 +679,7 @@ template <typename T>
 __global__ void actor_head_bwd_kernel(const float* __restrict__ out, long long ldo, const float* __restrict__ eps, const T* __restrict__ daction,
                                       long long ldda, const float* __restrict__ dent, float dent_scale, float* __restrict__ dout, long long lddo,
                                       long long rows, int A) {
+  genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   const float de = dent ? dent[i] * dent_scale : dent_scale;
@@ -683,6 +700,7 @@ __global__ void actor_head_bwd_kernel(const float* __restrict__ out, long long l
 // =================================================================================================
 __global__ void lambda_return_fwd_kernel(const float* __restrict__ reward, const float* __restrict__ value, float gamma, float lambda,
                                          float* __restrict__ target, int H, long long N) {
+  genrl::pdl_sync();
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float last = value[(long long)H * N + n];
@@ -696,6 +714,7 @@ __global__ void lambda_return_fwd_kernel(const float* __restrict__ reward, const
 // dtarget given as coef[t] (same for every n: the actor objective is a plain mean) or per-element array
 __global__ void lambda_return_bwd_kernel(const float* __restrict__ dtarget, const float* __restrict__ dt_scale, float gamma, float lambda,
                                          float* __restrict__ dreward, float* __restrict__ dvalue, int H, long long N) {
+  genrl::pdl_sync();
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float sc = dt_scale ? *dt_scale : 1.0f;
@@ -716,6 +735,7 @@ __global__ void lambda_return_bwd_kernel(const float* __restrict__ dtarget, cons
 //   like[r] = -sum_{chw} (mean - (u8/255 - 0.5))^2 ;  dmean = -2 (mean - x) * dlike[r] * scale
 // =================================================================================================
 __global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ mean, const uint8_t* __restrict__ obs, float* __restrict__ like, int E) {
+  genrl::pdl_sync();
   const long long r = blockIdx.x;
   float s = 0.f;
   for (int i = threadIdx.x; i < E; i += 256) {
@@ -731,6 +751,7 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ 
 }
 __global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ mean, const uint8_t* __restrict__ obs, const float* __restrict__ dlike,
                                                       const float* __restrict__ gscale, float scale, float* __restrict__ dmean, int E) {
+  genrl::pdl_sync();
   const long long r = blockIdx.x;
   const float g = (dlike ? dlike[r] : 1.0f) * scale * (gscale ? *gscale : 1.0f);
   for (int i = threadIdx.x; i < E; i += 256) {
@@ -744,6 +765,7 @@ __global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ 
 // =================================================================================================
 // out[0] = mean, out[1] = unbiased std (torch .std()), single block
 __global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  genrl::pdl_sync();
   __shared__ float red[32];
   __shared__ float s_mean;
   float s = 0.f;
@@ -766,6 +788,7 @@ __global__ void __launch_bounds__(1024) mean_std_kernel(const float* __restrict_
 // y[i] = a * x[i] + b   with optional device-side scalars (a_dev / b_dev) -> used for normalisation by RewardEMA
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = from_f32<TO>(to_f32(x[i]));
 }
@@ -774,6 +797,7 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long l
 template <typename TI, typename TO>
 __global__ void copy2d_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, long long rows, int cols,
                               const float* __restrict__ row_scale) {
+  genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   long long r = i / cols; int c = (int)(i % cols);
@@ -787,6 +811,7 @@ __global__ void copy2d_kernel(const TI* __restrict__ src, long long lds, TO* __r
 template <typename TI, typename TO>
 __global__ void gather_rows_kernel(const TI* __restrict__ src, long long lds, const int* __restrict__ idx, const float* __restrict__ scale,
                                    TO* __restrict__ dst, long long ldd, long long rows, int cols, int accumulate) {
+  genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   long long r = i / cols; int c = (int)(i % cols);
@@ -799,6 +824,7 @@ __global__ void gather_rows_kernel(const TI* __restrict__ src, long long lds, co
 // standard-normal fill (Box-Muller on Philox4x32-10): actor rsample noise, LAFITE noise of the connector
 __global__ void __launch_bounds__(256) fill_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
                                                           const unsigned long long* __restrict__ step_dev) {
+  genrl::pdl_sync();
   if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;
   const long long quads = (n + 3) / 4;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < quads; i += (long long)gridDim.x * 256) {
@@ -811,7 +837,8 @@ __global__ void __launch_bounds__(256) fill_normal_kernel(float* __restrict__ ou
     for (int k = 0; k < 4; ++k) if (i * 4 + k < n) out[i * 4 + k] = z[k];
   }
 }
-__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) { *c += inc; }
+__global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
+  genrl::pdl_sync(); *c += inc; }
 
 }  // namespace genrl
 
@@ -834,10 +861,10 @@ extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, cons
       const int lpr = ln_lpr(D, nch);
       const long long rpb = 8 * (32 / lpr);
       const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-      if (nch == 6) ln_fwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
-      else ln_fwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
+      if (nch == 6) genrl::launch_pdl(ln_fwd_fast_kernel<T, 6>, grid, 256, 0, ST(stream), (const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
+      else genrl::launch_pdl(ln_fwd_fast_kernel<T, 4>, grid, 256, 0, ST(stream), (const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D, lpr);
     } else {
-      ln_act_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D);
+      genrl::launch_pdl(ln_act_fwd_kernel<T>, row_grid(M, 148 * 16), THREADS, 0, ST(stream), (const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M, D);
     }
   });
   return check_launch("ln_act_fwd");
@@ -864,21 +891,21 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
           if (bps <= 0) bps = 1;
         }
         const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, (long long)num_sms_rows() * bps);
-        if (nch == 2) ln_bwd_colg_kernel<T, 2><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
+        if (nch == 2) genrl::launch_pdl(ln_bwd_colg_kernel<T, 2>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
                                                                              dgamma, dbeta, dlin_bias, M, D, lpr);
-        else ln_bwd_colg_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
+        else genrl::launch_pdl(ln_bwd_colg_kernel<T, 4>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx,
                                                                     dgamma, dbeta, dlin_bias, M, D, lpr);
       } else {
         const int nch = D <= 384 ? 6 : 4;
         const int lpr = ln_lpr(D, nch);
         const long long rpb = 8 * (32 / lpr);
         const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-        if (nch == 6) ln_bwd_fast_kernel<T, 6><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
-        else ln_bwd_fast_kernel<T, 4><<<grid, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+        if (nch == 6) genrl::launch_pdl(ln_bwd_fast_kernel<T, 6>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+        else genrl::launch_pdl(ln_bwd_fast_kernel<T, 4>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
       }
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      ln_act_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx,
+      genrl::launch_pdl(ln_act_bwd_kernel<T>, row_grid(M, 148 * 2), THREADS, smem, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx,
                                                                                 lddx, dgamma, dbeta, dlin_bias, M, D);
     }
   });
@@ -893,11 +920,11 @@ extern "C" int genrl_ln_colgrad(void* stream, const void* dy, long long lddy, co
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       dim3 g2(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
-      ln_colgrad_vec_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act,
+      genrl::launch_pdl(ln_colgrad_vec_kernel<T>, g2, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act,
                                                           dgamma, dbeta, dlin_bias, M, D);
     } else {
       dim3 g2(ceil_div(M, COL_RC), ceil_div(D, 32));
-      ln_colgrad_kernel<T><<<g2, 256, 0, ST(stream)>>>((const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act, dgamma,
+      genrl::launch_pdl(ln_colgrad_kernel<T>, g2, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, (const T*)dx, lddx, gamma, beta, stats, act, dgamma,
                                                       dbeta, dlin_bias, M, D);
     }
   });
@@ -909,10 +936,10 @@ extern "C" int genrl_colsum(void* stream, const void* x, long long ldx, float* o
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && vec_ok<T>(x, ldx)) {
       dim3 grid(ceil_div(M, COLV_ROWS), ceil_div(D, 128));
-      colsum_vec_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D);
+      genrl::launch_pdl(colsum_vec_kernel<T>, grid, 256, 0, ST(stream), (const T*)x, ldx, out, M, D);
     } else {
       dim3 grid(ceil_div(M, COL_RC), ceil_div(D, 32));
-      colsum_fast_kernel<T><<<grid, 256, 0, ST(stream)>>>((const T*)x, ldx, out, M, D);
+      genrl::launch_pdl(colsum_fast_kernel<T>, grid, 256, 0, ST(stream), (const T*)x, ldx, out, M, D);
     }
   });
   return check_launch("colsum");
@@ -924,9 +951,9 @@ extern "C" int genrl_gru_fwd(void* stream, const void* z, long long ldz, const f
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && vec_ok<T>(z, ldz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(hout, ldho) && (!hout_t || vec_ok<T>(hout_t, ldht)) &&
         f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-      gru_fwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
+      genrl::launch_pdl(gru_fwd_fast_kernel<T>, row_grid(M, 148 * 16), 256, 0, ST(stream), (const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
     } else {
-      gru_fwd_kernel<T><<<row_grid(M, 148 * 16), THREADS, 0, ST(stream)>>>((const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
+      genrl::launch_pdl(gru_fwd_kernel<T>, row_grid(M, 148 * 16), THREADS, 0, ST(stream), (const T*)z, ldz, gamma, beta, hprev, ldh, hout, ldho, (T*)hout_t, ldht, stats, M, D);
     }
   });
   return check_launch("gru_fwd");
@@ -942,14 +969,14 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
     if (!dgamma && D % 8 == 0 && vec_ok<T>(z, ldz) && vec_ok<T>(dz, lddz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(dh, lddh) &&
         (!dhprev || vec_ok<float>(dhprev, lddhp)) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       if (D == 1024)
-        gru_bwd_row1024_kernel<T><<<(int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
+        genrl::launch_pdl(gru_bwd_row1024_kernel<T>, (int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
                                                                                                (T*)dz, lddz, dhprev, lddhp, M);
       else
-        gru_bwd_fast_kernel<T><<<row_grid(M, 148 * 16), 256, 0, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+        genrl::launch_pdl(gru_bwd_fast_kernel<T>, row_grid(M, 148 * 16), 256, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
                                                                              dhprev, lddhp, M, D);
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(gru_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      gru_bwd_kernel<T><<<row_grid(M, 148 * 2), THREADS, smem, ST(stream)>>>(dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
+      genrl::launch_pdl(gru_bwd_kernel<T>, row_grid(M, 148 * 2), THREADS, smem, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
                                                                              dhprev, lddhp, dgamma, dbeta, M, D);
     }
   });
@@ -965,13 +992,13 @@ extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const floa
   if (fast_ok) {
     DISPATCH_T(dtype, {
       if (!stoch || vec_ok<T>(stoch, ld_stoch)) {
-        cat_sample_fwd_thr_kernel<T><<<ceil_div(rows * S, 128), 128, 0, ST(stream)>>>(logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
+        genrl::launch_pdl(cat_sample_fwd_thr_kernel<T>, ceil_div(rows * S, 128), 128, 0, ST(stream), logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
                                                                                      stoch32, ld_stoch32, idx, rows, S);
         return check_launch("cat_sample_fwd");
       }
     });
   }
-  DISPATCH_T(dtype, (cat_sample_fwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
+  DISPATCH_T(dtype, (genrl::launch_pdl(cat_sample_fwd_kernel<T>, row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream), logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
                                                                                                      stoch32, ld_stoch32, idx, rows, S, K)));
   return check_launch("cat_sample_fwd");
 }
@@ -983,12 +1010,12 @@ extern "C" int genrl_cat_sample_bwd(void* stream, const float* logit, const void
   if (K == CK && f32_vec_ok(logit) && f32_vec_ok(dlogit)) {
     DISPATCH_T(dtype, {
       if (vec_ok<T>(dstoch, ld_ds)) {
-        cat_sample_bwd_thr_kernel<T><<<ceil_div(rows * S, 128), 128, 0, ST(stream)>>>(logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S);
+        genrl::launch_pdl(cat_sample_bwd_thr_kernel<T>, ceil_div(rows * S, 128), 128, 0, ST(stream), logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S);
         return check_launch("cat_sample_bwd");
       }
     });
   }
-  DISPATCH_T(dtype, (cat_sample_bwd_kernel<T><<<row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream)>>>(logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S, K)));
+  DISPATCH_T(dtype, (genrl::launch_pdl(cat_sample_bwd_kernel<T>, row_grid(rows * S, 148 * 16), THREADS, 0, ST(stream), logit, (const T*)dstoch, ld_ds, sample, dlogit, accumulate, rows, S, K)));
   return check_launch("cat_sample_bwd");
 }
 
@@ -997,10 +1024,10 @@ extern "C" int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, fl
   GENRL_REQUIRE(K <= 32 * KPL, "kl: K=%d unsupported", K);
   cudaMemsetAsync(out4, 0, 4 * sizeof(float), ST(stream));
   if (S == 32 && K == CK && f32_vec_ok(lhs) && f32_vec_ok(rhs)) {
-    kl_fwd_thr_kernel<<<ceil_div(rows * 32, 128), 128, 0, ST(stream)>>>(lhs, rhs, free_bits, value, out4, rows);
+    genrl::launch_pdl(kl_fwd_thr_kernel, ceil_div(rows * 32, 128), 128, 0, ST(stream), lhs, rhs, free_bits, value, out4, rows);
     return check_launch("kl_fwd");
   }
-  kl_fwd_kernel<<<row_grid(rows, 148 * 4), THREADS, 0, ST(stream)>>>(lhs, rhs, free_bits, value, out4, rows, S, K);
+  genrl::launch_pdl(kl_fwd_kernel, row_grid(rows, 148 * 4), THREADS, 0, ST(stream), lhs, rhs, free_bits, value, out4, rows, S, K);
   return check_launch("kl_fwd");
 }
 
@@ -1008,68 +1035,68 @@ extern "C" int genrl_kl_bwd(void* stream, const float* lhs, const float* rhs, co
                             const float* gscale, float* dlhs, float* drhs, long long rows, int S, int K) {
   if (rows <= 0) return 0;
   if (S == 32 && K == CK && f32_vec_ok(lhs) && f32_vec_ok(rhs) && f32_vec_ok(dlhs) && f32_vec_ok(drhs)) {
-    kl_bwd_thr_kernel<<<ceil_div(rows * 32, 128), 128, 0, ST(stream)>>>(lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows);
+    genrl::launch_pdl(kl_bwd_thr_kernel, ceil_div(rows * 32, 128), 128, 0, ST(stream), lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows);
     return check_launch("kl_bwd");
   }
-  kl_bwd_kernel<<<row_grid(rows, 148 * 8), THREADS, 0, ST(stream)>>>(lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows, S, K);
+  genrl::launch_pdl(kl_bwd_kernel, row_grid(rows, 148 * 8), THREADS, 0, ST(stream), lhs, rhs, value, free_bits, w_lhs, w_rhs, gscale, dlhs, drhs, rows, S, K);
   return check_launch("kl_bwd");
 }
 
 extern "C" int genrl_twohot_fwd(void* stream, const float* logits, long long ldl, const float* x, int mode, float* out, long long rows) {
   if (rows <= 0) return 0;
-  twohot_fwd_kernel<<<row_grid(rows, 148 * 16), THREADS, 0, ST(stream)>>>(logits, ldl, x, mode, out, rows);
+  genrl::launch_pdl(twohot_fwd_kernel, row_grid(rows, 148 * 16), THREADS, 0, ST(stream), logits, ldl, x, mode, out, rows);
   return check_launch("twohot_fwd");
 }
 
 extern "C" int genrl_twohot_bwd(void* stream, const float* logits, long long ldl, const float* x, int mode, const float* dout, float scale,
                                 float* dlogits, long long lddl, long long rows) {
   if (rows <= 0) return 0;
-  twohot_bwd_kernel<<<row_grid(rows, 148 * 16), THREADS, 0, ST(stream)>>>(logits, ldl, x, mode, dout, scale, dlogits, lddl, rows);
+  genrl::launch_pdl(twohot_bwd_kernel, row_grid(rows, 148 * 16), THREADS, 0, ST(stream), logits, ldl, x, mode, dout, scale, dlogits, lddl, rows);
   return check_launch("twohot_bwd");
 }
 
 extern "C" int genrl_actor_head_fwd(void* stream, const float* out, long long ldo, const float* eps, int use_mean, float* action, long long lda,
                                     void* action_t, long long ldat, float* ent, long long rows, int A, int dtype) {
   if (rows <= 0) return 0;
-  DISPATCH_T(dtype, (actor_head_fwd_kernel<T><<<ceil_div(rows, 128), 128, 0, ST(stream)>>>(out, ldo, eps, use_mean, action, lda, (T*)action_t, ldat, ent, rows, A)));
+  DISPATCH_T(dtype, (genrl::launch_pdl(actor_head_fwd_kernel<T>, ceil_div(rows, 128), 128, 0, ST(stream), out, ldo, eps, use_mean, action, lda, (T*)action_t, ldat, ent, rows, A)));
   return check_launch("actor_head_fwd");
 }
 
 extern "C" int genrl_actor_head_bwd(void* stream, const float* out, long long ldo, const float* eps, const void* daction, long long ldda,
                                     const float* dent, float dent_scale, float* dout, long long lddo, long long rows, int A, int dtype) {
   if (rows <= 0) return 0;
-  DISPATCH_T(dtype, (actor_head_bwd_kernel<T><<<ceil_div(rows, 128), 128, 0, ST(stream)>>>(out, ldo, eps, (const T*)daction, ldda, dent, dent_scale, dout, lddo, rows, A)));
+  DISPATCH_T(dtype, (genrl::launch_pdl(actor_head_bwd_kernel<T>, ceil_div(rows, 128), 128, 0, ST(stream), out, ldo, eps, (const T*)daction, ldda, dent, dent_scale, dout, lddo, rows, A)));
   return check_launch("actor_head_bwd");
 }
 
 extern "C" int genrl_lambda_return_fwd(void* stream, const float* reward, const float* value, float gamma, float lambda, float* target, int H, long long N) {
   if (N <= 0) return 0;
-  lambda_return_fwd_kernel<<<ceil_div(N, 128), 128, 0, ST(stream)>>>(reward, value, gamma, lambda, target, H, N);
+  genrl::launch_pdl(lambda_return_fwd_kernel, ceil_div(N, 128), 128, 0, ST(stream), reward, value, gamma, lambda, target, H, N);
   return check_launch("lambda_return_fwd");
 }
 
 extern "C" int genrl_lambda_return_bwd(void* stream, const float* dtarget, const float* dt_scale, float gamma, float lambda, float* dreward,
                                        float* dvalue, int H, long long N) {
   if (N <= 0) return 0;
-  lambda_return_bwd_kernel<<<ceil_div(N, 128), 128, 0, ST(stream)>>>(dtarget, dt_scale, gamma, lambda, dreward, dvalue, H, N);
+  genrl::launch_pdl(lambda_return_bwd_kernel, ceil_div(N, 128), 128, 0, ST(stream), dtarget, dt_scale, gamma, lambda, dreward, dvalue, H, N);
   return check_launch("lambda_return_bwd");
 }
 
 extern "C" int genrl_mse_fwd(void* stream, const float* mean, const unsigned char* obs, float* like, long long rows, int E) {
   if (rows <= 0) return 0;
-  mse_fwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(mean, obs, like, E);
+  genrl::launch_pdl(mse_fwd_kernel, (unsigned)rows, 256, 0, ST(stream), mean, obs, like, E);
   return check_launch("mse_fwd");
 }
 
 extern "C" int genrl_mse_bwd(void* stream, const float* mean, const unsigned char* obs, const float* dlike, const float* gscale, float scale,
                              float* dmean, long long rows, int E) {
   if (rows <= 0) return 0;
-  mse_bwd_kernel<<<(unsigned)rows, 256, 0, ST(stream)>>>(mean, obs, dlike, gscale, scale, dmean, E);
+  genrl::launch_pdl(mse_bwd_kernel, (unsigned)rows, 256, 0, ST(stream), mean, obs, dlike, gscale, scale, dmean, E);
   return check_launch("mse_bwd");
 }
 
 extern "C" int genrl_mean_std(void* stream, const float* x, long long n, float* out2) {
-  mean_std_kernel<<<1, 1024, 0, ST(stream)>>>(x, n, out2);
+  genrl::launch_pdl(mean_std_kernel, 1, 1024, 0, ST(stream), x, n, out2);
   return check_launch("mean_std");
 }
 
@@ -1080,7 +1107,7 @@ static bool try_fast_gather(cudaStream_t st, const void* src, long long lds, con
   if (cols % 8 != 0 || !vec_ok<TI>(src, lds) || !vec_ok<TO>(dst, ldd)) return false;
   const long long total = rows * (cols / 8);
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
-  gather_rows_fast_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols / 8, accumulate);
+  genrl::launch_pdl(gather_rows_fast_kernel<TI, TO>, grid, 256, 0, st, (const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols / 8, accumulate);
   return true;
 }
 
@@ -1089,7 +1116,7 @@ static void run_gather(cudaStream_t st, const void* src, long long lds, const in
                        int cols, int accumulate) {
   if (try_fast_gather<TI, TO>(st, src, lds, idx, scale, dst, ldd, rows, cols, accumulate)) return;
   unsigned grid = (unsigned)ceil_div(rows * cols, 256);
-  gather_rows_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols, accumulate);
+  genrl::launch_pdl(gather_rows_kernel<TI, TO>, grid, 256, 0, st, (const TI*)src, lds, idx, scale, (TO*)dst, ldd, rows, cols, accumulate);
 }
 
 extern "C" int genrl_gather_rows(void* stream, const void* src, long long lds, int src_dtype, const int* idx, const float* scale, void* dst,
@@ -1113,11 +1140,11 @@ extern "C" int genrl_fill_normal(void* stream, float* out, long long n, unsigned
                                  const unsigned long long* step_dev) {
   if (n <= 0) return 0;
   unsigned grid = (unsigned)std::min<long long>(((n + 3) / 4 + 255) / 256, 148 * 16);
-  fill_normal_kernel<<<grid, 256, 0, ST(stream)>>>(out, n, seed, offset, step_dev);
+  genrl::launch_pdl(fill_normal_kernel, grid, 256, 0, ST(stream), out, n, seed, offset, step_dev);
   return check_launch("fill_normal");
 }
 
 extern "C" int genrl_counter_add(void* stream, unsigned long long* counter, unsigned long long inc) {
-  counter_add_kernel<<<1, 1, 0, ST(stream)>>>(counter, inc);
+  genrl::launch_pdl(counter_add_kernel, 1, 1, 0, ST(stream), counter, inc);
   return check_launch("counter_add");
 }

@@ -79,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  genrl::pdl_sync();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -263,6 +264,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  genrl::pdl_sync();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -468,6 +470,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  genrl::pdl_sync();      // everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail
 
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
   const int half = warp >= 6 ? 1 : 0;           // warps 2..5: columns 0..63, warps 6..9: columns 64..127
@@ -590,6 +593,7 @@ struct SimtParams {
 };
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtParams p) {
+  genrl::pdl_sync();
   __shared__ float As[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
   const int tid = threadIdx.x;
@@ -664,7 +668,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, TcParams p, i
     attr_set = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, TC_BM), splits);
-  kern<<<grid, TC_THREADS, SMEM, st>>>(ta, tb, p);
+  genrl::launch_pdl(kern, grid, TC_THREADS, SMEM, st, ta, tb, p);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -742,7 +746,7 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
     p.swn = transW ? 1 : ldw; p.swk = transW ? ldw : 1;
     p.C = reinterpret_cast<float*>(C); p.ldc = (int)ldc; p.bias = bias; p.accumulate = accumulate;
     dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+    genrl::launch_pdl(gemm_simt_kernel, grid, 256, 0, st, p);
     return check_launch("gemm_simt_kernel");
   }
   GENRL_REQUIRE(in_dtype == GENRL_BF16, "genrl_gemm: unknown operand dtype %d", in_dtype);
@@ -770,10 +774,10 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
     const int grid = std::min(tiles, num_sms());
     if (!transW) {
       if (!attr_set[0]) { cudaFuncSetAttribute(gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set[0] = true; }
-      gemm_tc_persist_kernel<false><<<grid, PG_THREADS, SMEM, st>>>(pa, pb, q);
+      genrl::launch_pdl(gemm_tc_persist_kernel<false>, grid, PG_THREADS, SMEM, st, pa, pb, q);
     } else {
       if (!attr_set[1]) { cudaFuncSetAttribute(gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); attr_set[1] = true; }
-      gemm_tc_persist_kernel<true><<<grid, PG_THREADS, SMEM, st>>>(pa, pb, q);
+      genrl::launch_pdl(gemm_tc_persist_kernel<true>, grid, PG_THREADS, SMEM, st, pa, pb, q);
     }
     return check_launch("gemm_tc_persist_kernel");
   }
@@ -837,10 +841,12 @@ extern "C" int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* 
   cfg.blockDim = dim3(LN_THREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = N / 128; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (getenv("GENRL_GEMM_DEBUG")) {
     int ncl = -1;
     cudaError_t eo = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);

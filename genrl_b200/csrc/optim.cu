@@ -6,6 +6,7 @@
 namespace genrl {
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  genrl::pdl_sync();
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { float v = g[i]; s += v * v; }
   __shared__ float red[8];
@@ -16,6 +17,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 }
 
 __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, long long n, float s) {
+  genrl::pdl_sync();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] *= s;
 }
 
@@ -23,6 +25,7 @@ __global__ void __launch_bounds__(256) scale_kernel(float* __restrict__ p, long 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    long long n, float lr, float eps, float clip, const float* __restrict__ sumsq,
                                                    const float* __restrict__ state, float decay) {
+  genrl::pdl_sync();
   const float norm = sqrtf(*sumsq);
   const float coef = clip > 0.f ? fminf(clip / (norm + 1e-6f), 1.0f) : 1.0f;
   const float t = state[0] + 1.0f;
@@ -41,6 +44,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
 }
 
 __global__ void adam_finish_kernel(float* state, const float* sumsq) {
+  genrl::pdl_sync();
   state[0] += 1.0f;
   state[1] = sqrtf(*sumsq);
 }
@@ -59,6 +63,7 @@ struct PackEntry {
 
 template <typename TO>
 __global__ void __launch_bounds__(256) pack_kernel(const PackEntry* __restrict__ table) {
+  genrl::pdl_sync();
   const PackEntry e = table[blockIdx.y];
   TO* dst = reinterpret_cast<TO*>(e.dst);
   if (e.kind == 0) {
@@ -87,6 +92,7 @@ __device__ __forceinline__ float key2f(uint32_t k) { uint32_t u = (k & 0x8000000
 // ema[0:2] <- alpha*q + (1-alpha)*ema ; out[0]=offset(ema[0]) out[1]=scale=max(ema[1]-ema[0],1) out[2..3] = raw quantiles
 __global__ void __launch_bounds__(1024) quantile_ema_kernel(const float* __restrict__ x, long long n, float q_lo, float q_hi, float alpha,
                                                             float* __restrict__ ema, float* __restrict__ out) {
+  genrl::pdl_sync();
   __shared__ unsigned hist[4][256];
   __shared__ uint32_t prefix[4];
   __shared__ long long rank[4];
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(1024) quantile_ema_kernel(const float* __restr
 // out[0]=loss, out[1]=mean normed target (all t), out[2]=std normed target, out[3]=mean ent ; dcoef[0] = -1/((H-1) N scale)
 __global__ void __launch_bounds__(1024) actor_objective_kernel(const float* __restrict__ target, const float* __restrict__ ent, const float* __restrict__ offscale,
                                                                float ent_scale, int H, long long N, float* __restrict__ out, float* __restrict__ dcoef) {
+  genrl::pdl_sync();
   __shared__ double red[3][32];
   const float off = offscale[0], sc = offscale[1];
   double s_all = 0.0, s_obj = 0.0, s_ent = 0.0;
@@ -175,6 +182,7 @@ __global__ void __launch_bounds__(1024) actor_objective_kernel(const float* __re
 
 // out[0] (+)= scale * sum(x) / n    (weighted means of per-row log-likelihoods -> scalar losses)
 __global__ void __launch_bounds__(1024) mean_scale_kernel(const float* __restrict__ x, long long n, float scale, float* __restrict__ out, int accumulate) {
+  genrl::pdl_sync();
   __shared__ double red[32];
   double s = 0.0;
   for (long long i = threadIdx.x; i < n; i += 1024) s += x[i];
@@ -197,13 +205,13 @@ using namespace genrl;
 // sumsq_out[0] (+)= sum g^2
 extern "C" int genrl_grad_sumsq(void* stream, const float* g, long long n, float* sumsq_out, int zero_first) {
   if (zero_first) cudaMemsetAsync(sumsq_out, 0, sizeof(float), ST(stream));
-  if (n > 0) sumsq_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(g, n, sumsq_out);
+  if (n > 0) genrl::launch_pdl(sumsq_kernel, grid_for(n), 256, 0, ST(stream), g, n, sumsq_out);
   return check_launch("grad_sumsq");
 }
 
 extern "C" int genrl_scale(void* stream, float* p, long long n, float s) {
   if (n <= 0) return 0;
-  scale_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, n, s);
+  genrl::launch_pdl(scale_kernel, grid_for(n), 256, 0, ST(stream), p, n, s);
   return check_launch("scale");
 }
 
@@ -211,8 +219,8 @@ extern "C" int genrl_scale(void* stream, float* p, long long n, float s) {
 // state: device float[2] {step, last grad norm}; `finish` bumps the step (set on the last segment of a call).
 extern "C" int genrl_adam_step(void* stream, float* p, float* g, float* m, float* v, long long n, float lr, float eps, float clip,
                                const float* sumsq, float* state, int finish, float decay) {
-  if (n > 0) adam_kernel<<<grid_for(n), 256, 0, ST(stream)>>>(p, g, m, v, n, lr, eps, clip, sumsq, state, decay);
-  if (finish) adam_finish_kernel<<<1, 1, 0, ST(stream)>>>(state, sumsq);
+  if (n > 0) genrl::launch_pdl(adam_kernel, grid_for(n), 256, 0, ST(stream), p, g, m, v, n, lr, eps, clip, sumsq, state, decay);
+  if (finish) genrl::launch_pdl(adam_finish_kernel, 1, 1, 0, ST(stream), state, sumsq);
   return check_launch("adam_step");
 }
 
@@ -220,26 +228,26 @@ extern "C" int genrl_adam_step(void* stream, float* p, float* g, float* m, float
 extern "C" int genrl_pack_weights(void* stream, const void* table, int n_entries, int dst_dtype) {
   if (n_entries <= 0) return 0;
   dim3 grid(148 * 2, n_entries);
-  if (dst_dtype == GENRL_F32) pack_kernel<float><<<grid, 256, 0, ST(stream)>>>((const PackEntry*)table);
-  else pack_kernel<__nv_bfloat16><<<grid, 256, 0, ST(stream)>>>((const PackEntry*)table);
+  if (dst_dtype == GENRL_F32) genrl::launch_pdl(pack_kernel<float>, grid, 256, 0, ST(stream), (const PackEntry*)table);
+  else genrl::launch_pdl(pack_kernel<__nv_bfloat16>, grid, 256, 0, ST(stream), (const PackEntry*)table);
   return check_launch("pack_weights");
 }
 extern "C" int genrl_pack_entry_size() { return (int)sizeof(PackEntry); }
 
 extern "C" int genrl_quantile_ema(void* stream, const float* x, long long n, float q_lo, float q_hi, float alpha, float* ema, float* out4) {
   GENRL_REQUIRE(n > 0, "quantile_ema: empty input");
-  quantile_ema_kernel<<<1, 1024, 0, ST(stream)>>>(x, n, q_lo, q_hi, alpha, ema, out4);
+  genrl::launch_pdl(quantile_ema_kernel, 1, 1024, 0, ST(stream), x, n, q_lo, q_hi, alpha, ema, out4);
   return check_launch("quantile_ema");
 }
 
 extern "C" int genrl_actor_objective(void* stream, const float* target, const float* ent, const float* offscale, float ent_scale, int H, long long N,
                                      float* out4, float* dcoef) {
-  actor_objective_kernel<<<1, 1024, 0, ST(stream)>>>(target, ent, offscale, ent_scale, H, N, out4, dcoef);
+  genrl::launch_pdl(actor_objective_kernel, 1, 1024, 0, ST(stream), target, ent, offscale, ent_scale, H, N, out4, dcoef);
   return check_launch("actor_objective");
 }
 
 extern "C" int genrl_mean_scale(void* stream, const float* x, long long n, float scale, float* out, int accumulate) {
   GENRL_REQUIRE(n > 0, "mean_scale: empty input");
-  mean_scale_kernel<<<1, 1024, 0, ST(stream)>>>(x, n, scale, out, accumulate);
+  genrl::launch_pdl(mean_scale_kernel, 1, 1024, 0, ST(stream), x, n, scale, out, accumulate);
   return check_launch("mean_scale");
 }

@@ -13,6 +13,7 @@ namespace genrl {
 // dst[b, :] (span_bytes) = src[start[b] * row_bytes : ... + span_bytes];  16-byte vector path when everything is aligned
 __global__ void __launch_bounds__(256) replay_gather_kernel(const unsigned char* __restrict__ src, const long long* __restrict__ start, long long row_bytes,
                                                             long long span_bytes, unsigned char* __restrict__ dst, int chunks_per_span, int vec) {
+  genrl::pdl_sync();
   const int b = blockIdx.x / chunks_per_span;
   const int c = blockIdx.x % chunks_per_span;
   const unsigned char* s = src + start[b] * row_bytes;
@@ -42,7 +43,7 @@ extern "C" int genrl_replay_gather(void* stream, const void* store, const long l
   long long per = (span + chunks - 1) / chunks;
   const bool aligned = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(store) % 16 == 0) && (reinterpret_cast<uintptr_t>(batch) % 16 == 0);
   if (aligned && per % 16 != 0) { per = (per + 15) / 16 * 16; chunks = (int)((span + per - 1) / per); }
-  replay_gather_kernel<<<(unsigned)(B * chunks), 256, 0, ST(stream)>>>((const unsigned char*)store, start, row_bytes, span, (unsigned char*)batch, chunks,
+  genrl::launch_pdl(replay_gather_kernel, (unsigned)(B * chunks), 256, 0, ST(stream), (const unsigned char*)store, start, row_bytes, span, (unsigned char*)batch, chunks,
                                                                       aligned ? 1 : 0);
   return check_launch("replay_gather");
 }

@@ -55,6 +55,7 @@ template <typename T, int FAST_NCH>
 __global__ void __launch_bounds__(256, (FAST_NCH == 4 ? 4 : 2)) ln_fwd_fast_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, int act, T* __restrict__ y, long long ldy,
                                                           float* __restrict__ stats, long long M, int D, int lpr) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31, sub = lane % lpr, rwi = lane / lpr, rpw = 32 / lpr;
   const long long wstride = (long long)gridDim.x * 8 * rpw;
   for (long long base = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw; base < M; base += wstride) {
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const T* __restrict
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
                                                           long long M, int D, int lpr) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31, sub = lane % lpr, rwi = lane / lpr, rpw = 32 / lpr;
   const long long wstride = (long long)gridDim.x * 8 * rpw;
   for (long long base = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw; base < M; base += wstride) {
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(256, (FAST_NCH <= 2 ? 2 : 1)) ln_bwd_colg_kern
                                                           const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlb,
                                                           long long M, int D, int lpr) {
+  genrl::pdl_sync();
   __shared__ float red[3 * 1024];
   for (int i = threadIdx.x; i < 3 * D; i += 256) red[i] = 0.f;
   __syncthreads();
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(256) ln_colgrad_kernel(const T* __restrict__ d
                                                          const T* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, const float* __restrict__ stats, int act,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlb, long long M, int D) {
+  genrl::pdl_sync();
   __shared__ float red[3][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
@@ -289,6 +293,7 @@ __global__ void __launch_bounds__(256) ln_colgrad_kernel(const T* __restrict__ d
 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_fast_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, long long M, int D) {
+  genrl::pdl_sync();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + tx;
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(256) ln_colgrad_vec_kernel(const T* __restrict
                                                              const T* __restrict__ dx, long long lddx, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ stats, int act,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dlb, long long M, int D) {
+  genrl::pdl_sync();
   __shared__ float red[3][16][129];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c = blockIdx.y * 128 + tx * 8;
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(256) ln_colgrad_vec_kernel(const T* __restrict
 
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long ldx, float* __restrict__ out, long long M, int D) {
+  genrl::pdl_sync();
   __shared__ float red[16][129];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int c = blockIdx.y * 128 + tx * 8;
@@ -411,6 +418,7 @@ __global__ void __launch_bounds__(256) gru_fwd_fast_kernel(const T* __restrict__
                                                            const float* __restrict__ beta, const float* __restrict__ hprev, long long ldh,
                                                            float* __restrict__ hout, long long ldho, T* __restrict__ hout_t, long long ldht,
                                                            float* __restrict__ stats, long long M, int D) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int D3 = 3 * D;
   for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(256) gru_bwd_fast_kernel(const float* __restri
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
                                                            T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M, int D) {
+  genrl::pdl_sync();
   const int lane = threadIdx.x & 31;
   const int D3 = 3 * D;
   for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
                                                               T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M) {
+  genrl::pdl_sync();
   constexpr int D = 1024, D3 = 3072;
   __shared__ float red[2][4];
   const int j = threadIdx.x * 8, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -531,6 +541,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gather_rows_fast_kernel(const TI* __restrict__ src, long long lds, const int* __restrict__ idx,
                                                                const float* __restrict__ scale, TO* __restrict__ dst, long long ldd, long long rows,
                                                                int cols8, int accumulate) {
+  genrl::pdl_sync();
   const long long total = rows * cols8;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long r = i / cols8; const int c = (int)(i % cols8) * 8;

@@ -201,6 +201,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 // MMA = true: bf16 tensor-core mat-vec (weights resident as bf16, h read from the bf16 hprev_t rows); false: fp32 FFMA.
 template <bool MMA>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_fwd_kernel(ScanFwdParams p) {
+  genrl::pdl_sync();
   extern __shared__ float smem[];
   const int D = p.D, D3 = 3 * p.D, B = p.B, T = p.T, G = p.G;
   constexpr int R = 3 * SCAN_U;
@@ -396,6 +397,7 @@ __device__ __forceinline__ ScanBwdIn scan_bwd_load(const ScanBwdParams& p, int b
 
 template <bool MMA>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) rssm_scan_bwd_kernel(ScanBwdParams p) {
+  genrl::pdl_sync();
   extern __shared__ float smem[];
   const int D = p.D, D3 = 3 * p.D, B = p.B, T = p.T, G = p.G;
   constexpr int R = 3 * SCAN_U;

@@ -1,6 +1,7 @@
 // Error plumbing + small utilities of the C-ABI (see include/genrl_b200.h).
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace genrl {
 
@@ -23,6 +24,15 @@ int check_launch(const char* what) {
 }
 
 static long long g_launches = 0;
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GENRL_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 }  // namespace genrl
 

@@ -72,6 +72,7 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(TC_PIX) conv0_fwd_kernel(const uint8_t* __restrict__ obs, const float* __restrict__ w, const float* __restrict__ bias,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                            T* __restrict__ y, float* __restrict__ stats, long long M, int H, int W, int Ho, int Wo) {
+  genrl::pdl_sync();
   __shared__ __align__(16) float ws[48 * CH];
   load_w0<CH>(w, ws);                   // once per (persistent) block
   __syncthreads();
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(TC_PIX) conv0_bwd_kernel(const uint8_t* __rest
                                                            const float* __restrict__ stats, const T* __restrict__ dy, float* __restrict__ dW,
                                                            float* __restrict__ db, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            long long M, int H, int W, int Ho, int Wo) {
+  genrl::pdl_sync();
   extern __shared__ __align__(16) float smem0[];
   float* ws = smem0;                     // [48][CH]
   constexpr int PS = 49, DS = CH + 1;    // odd row strides: conflict-free per-thread row writes
@@ -213,6 +215,7 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(256) convT3_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          const uint8_t* __restrict__ obs, float* __restrict__ mean_out, float* __restrict__ like,
                                                          long long items, int Hi, int Wi, int Ho, int Wo) {
+  genrl::pdl_sync();
   __shared__ float4 ws[TC_KT * TC_KT * CH];          // [kh][kw][ci] -> (co0, co1, co2, 0)
   for (int i = threadIdx.x; i < TC_KT * TC_KT * CH; i += 256) {
     const int ci = i % CH, kk = i / CH, kh = kk / TC_KT, kw = kk % TC_KT;
@@ -286,6 +289,7 @@ template <typename T, int CH>
 __global__ void __launch_bounds__(TC_PIX) convT3_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ mean,
                                                             const uint8_t* __restrict__ obs, const float* __restrict__ dlike, T* __restrict__ dx,
                                                             float* __restrict__ dW, float* __restrict__ db, long long Mi, int Hi, int Wi, int Ho, int Wo) {
+  genrl::pdl_sync();
   constexpr int NJ = 3 * TC_KT * TC_KT;                // 108 = (co, kh, kw)
   constexpr int JG = 14, CG = 3;                       // thread owns 3 ci x 14 j of dW: 16 ci-groups x 8 j-groups
   extern __shared__ __align__(16) float smemT[];
@@ -397,8 +401,8 @@ extern "C" int genrl_conv0_ln_silu_fwd(void* stream, const unsigned char* obs, c
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0) return 0;
   const unsigned grid = (unsigned)((M + TC_PIX - 1) / TC_PIX);
-  if (dtype == GENRL_BF16) conv0_fwd_kernel<__nv_bfloat16, 48><<<grid, TC_PIX, 0, ST(stream)>>>(obs, w, bias, gamma, beta, eps, (__nv_bfloat16*)y, stats, M, H, W, Ho, Wo);
-  else conv0_fwd_kernel<float, 48><<<grid, TC_PIX, 0, ST(stream)>>>(obs, w, bias, gamma, beta, eps, (float*)y, stats, M, H, W, Ho, Wo);
+  if (dtype == GENRL_BF16) genrl::launch_pdl(conv0_fwd_kernel<__nv_bfloat16, 48>, grid, TC_PIX, 0, ST(stream), obs, w, bias, gamma, beta, eps, (__nv_bfloat16*)y, stats, M, H, W, Ho, Wo);
+  else genrl::launch_pdl(conv0_fwd_kernel<float, 48>, grid, TC_PIX, 0, ST(stream), obs, w, bias, gamma, beta, eps, (float*)y, stats, M, H, W, Ho, Wo);
   return check_launch("conv0_ln_silu_fwd");
 }
 
@@ -414,10 +418,10 @@ extern "C" int genrl_conv0_ln_silu_bwd(void* stream, const unsigned char* obs, c
   const unsigned grid = (unsigned)std::min<long long>((M + TC_PIX - 1) / TC_PIX, (long long)sm_count() * 3);
   if (dtype == GENRL_BF16) {
     cudaFuncSetAttribute(conv0_bwd_kernel<__nv_bfloat16, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv0_bwd_kernel<__nv_bfloat16, 48><<<grid, TC_PIX, smem, ST(stream)>>>(obs, w, bias, gamma, beta, stats, (const __nv_bfloat16*)dy, dW, db, dgamma, dbeta, M, H, W, Ho, Wo);
+    genrl::launch_pdl(conv0_bwd_kernel<__nv_bfloat16, 48>, grid, TC_PIX, smem, ST(stream), obs, w, bias, gamma, beta, stats, (const __nv_bfloat16*)dy, dW, db, dgamma, dbeta, M, H, W, Ho, Wo);
   } else {
     cudaFuncSetAttribute(conv0_bwd_kernel<float, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv0_bwd_kernel<float, 48><<<grid, TC_PIX, smem, ST(stream)>>>(obs, w, bias, gamma, beta, stats, (const float*)dy, dW, db, dgamma, dbeta, M, H, W, Ho, Wo);
+    genrl::launch_pdl(conv0_bwd_kernel<float, 48>, grid, TC_PIX, smem, ST(stream), obs, w, bias, gamma, beta, stats, (const float*)dy, dW, db, dgamma, dbeta, M, H, W, Ho, Wo);
   }
   return check_launch("conv0_ln_silu_bwd");
 }
@@ -431,8 +435,8 @@ extern "C" int genrl_convT3_mse_fwd(void* stream, const void* x, const float* w,
   if (total <= 0) return 0;
   cudaMemsetAsync(like, 0, (size_t)N * sizeof(float), ST(stream));
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count() * 8);
-  if (dtype == GENRL_BF16) convT3_fwd_kernel<__nv_bfloat16, 48><<<grid, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x, w, bias, obs, mean_out, like, total, Hi, Wi, Ho, Wo);
-  else convT3_fwd_kernel<float, 48><<<grid, 256, 0, ST(stream)>>>((const float*)x, w, bias, obs, mean_out, like, total, Hi, Wi, Ho, Wo);
+  if (dtype == GENRL_BF16) genrl::launch_pdl(convT3_fwd_kernel<__nv_bfloat16, 48>, grid, 256, 0, ST(stream), (const __nv_bfloat16*)x, w, bias, obs, mean_out, like, total, Hi, Wi, Ho, Wo);
+  else genrl::launch_pdl(convT3_fwd_kernel<float, 48>, grid, 256, 0, ST(stream), (const float*)x, w, bias, obs, mean_out, like, total, Hi, Wi, Ho, Wo);
   return check_launch("convT3_mse_fwd");
 }
 
@@ -447,10 +451,10 @@ extern "C" int genrl_convT3_mse_bwd(void* stream, const void* x, const float* w,
   const unsigned grid = (unsigned)std::min<long long>((Mi + TC_PIX - 1) / TC_PIX, (long long)sm_count() * 2);
   if (dtype == GENRL_BF16) {
     cudaFuncSetAttribute(convT3_bwd_kernel<__nv_bfloat16, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    convT3_bwd_kernel<__nv_bfloat16, 48><<<grid, TC_PIX, smem, ST(stream)>>>((const __nv_bfloat16*)x, w, mean, obs, dlike, (__nv_bfloat16*)dx, dW, db, Mi, Hi, Wi, Ho, Wo);
+    genrl::launch_pdl(convT3_bwd_kernel<__nv_bfloat16, 48>, grid, TC_PIX, smem, ST(stream), (const __nv_bfloat16*)x, w, mean, obs, dlike, (__nv_bfloat16*)dx, dW, db, Mi, Hi, Wi, Ho, Wo);
   } else {
     cudaFuncSetAttribute(convT3_bwd_kernel<float, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    convT3_bwd_kernel<float, 48><<<grid, TC_PIX, smem, ST(stream)>>>((const float*)x, w, mean, obs, dlike, (float*)dx, dW, db, Mi, Hi, Wi, Ho, Wo);
+    genrl::launch_pdl(convT3_bwd_kernel<float, 48>, grid, TC_PIX, smem, ST(stream), (const float*)x, w, mean, obs, dlike, (float*)dx, dW, db, Mi, Hi, Wi, Ho, Wo);
   }
   return check_launch("convT3_mse_bwd");
 }

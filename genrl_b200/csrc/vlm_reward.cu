@@ -37,6 +37,7 @@ __device__ __forceinline__ float maxcos_from(float uv, float uu, float vv) {
 template <typename T>
 __global__ void __launch_bounds__(VR_THREADS) vlm_reward_fwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, float* __restrict__ reward,
                                                                     int* __restrict__ shift, int Tn, long long N, int E, int F, int align) {
+  genrl::pdl_sync();
   const long long n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VR_THREADS / 32;
   __shared__ float score[VR_MAX_T];
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(VR_THREADS) vlm_reward_fwd_kernel(const T* __r
 template <typename T>
 __global__ void __launch_bounds__(VR_THREADS) vlm_reward_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const int* __restrict__ shift,
                                                                     const float* __restrict__ dreward, T* __restrict__ dpa, int Tn, long long N, int E) {
+  genrl::pdl_sync();
   const long long n = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = VR_THREADS / 32;
   const int b = shift[n];
@@ -109,9 +111,9 @@ extern "C" int genrl_vlm_reward_fwd(void* stream, const void* pa, const void* pt
   GENRL_REQUIRE(T <= VR_MAX_T, "vlm_reward: T = %d exceeds %d", T, VR_MAX_T);
   GENRL_REQUIRE(!align || T > n_frames, "vlm_reward: align_sequence needs more than n_frames = %d steps, got %d", n_frames, T);
   if (dtype == GENRL_F32)
-    vlm_reward_fwd_kernel<float><<<(unsigned)N, VR_THREADS, 0, ST(stream)>>>((const float*)pa, (const float*)pt, reward, shift, T, N, E, n_frames, align);
+    genrl::launch_pdl(vlm_reward_fwd_kernel<float>, (unsigned)N, VR_THREADS, 0, ST(stream), (const float*)pa, (const float*)pt, reward, shift, T, N, E, n_frames, align);
   else
-    vlm_reward_fwd_kernel<__nv_bfloat16><<<(unsigned)N, VR_THREADS, 0, ST(stream)>>>((const __nv_bfloat16*)pa, (const __nv_bfloat16*)pt, reward, shift,
+    genrl::launch_pdl(vlm_reward_fwd_kernel<__nv_bfloat16>, (unsigned)N, VR_THREADS, 0, ST(stream), (const __nv_bfloat16*)pa, (const __nv_bfloat16*)pt, reward, shift,
                                                                                     T, N, E, n_frames, align);
   return check_launch("vlm_reward_fwd");
 }
@@ -120,9 +122,9 @@ extern "C" int genrl_vlm_reward_bwd(void* stream, const void* pa, const void* pt
                                     int E, int dtype) {
   if (N <= 0 || T <= 0) return 0;
   if (dtype == GENRL_F32)
-    vlm_reward_bwd_kernel<float><<<(unsigned)N, VR_THREADS, 0, ST(stream)>>>((const float*)pa, (const float*)pt, shift, dreward, (float*)dpa, T, N, E);
+    genrl::launch_pdl(vlm_reward_bwd_kernel<float>, (unsigned)N, VR_THREADS, 0, ST(stream), (const float*)pa, (const float*)pt, shift, dreward, (float*)dpa, T, N, E);
   else
-    vlm_reward_bwd_kernel<__nv_bfloat16><<<(unsigned)N, VR_THREADS, 0, ST(stream)>>>((const __nv_bfloat16*)pa, (const __nv_bfloat16*)pt, shift, dreward,
+    genrl::launch_pdl(vlm_reward_bwd_kernel<__nv_bfloat16>, (unsigned)N, VR_THREADS, 0, ST(stream), (const __nv_bfloat16*)pa, (const __nv_bfloat16*)pt, shift, dreward,
                                                                                     (__nv_bfloat16*)dpa, T, N, E);
   return check_launch("vlm_reward_bwd");
 }
