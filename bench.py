@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
+    ap.add_argument("--rollout-streams", type=int, default=2, help="row chunks of the imagination rollout enqueued on separate CUDA streams")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: fp16 autocast (the reference's precision: 16)")
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: sample size in sequences (default REF_SAMPLE_B)")
@@ -210,6 +211,7 @@ def run_native(args):
     cfg, obs_space, act_spec = make_cfg(args, dev, args.precision)
     cfg.cuda_graph = not args.eager
     cfg.overlap_streams = not args.no_overlap
+    cfg.rollout_streams = 1 if args.no_overlap else args.rollout_streams
     torch.manual_seed(1)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):

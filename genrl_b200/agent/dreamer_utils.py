@@ -692,10 +692,11 @@ class Optimizer:
 _SIDE_STREAMS = {}
 
 
-def side_stream(device):
-    """second CUDA stream per device: independent kernel chains (connector vs world-model backward, critic vs actor backward)
-    are enqueued there so their latency-bound small kernels fill the SMs the other chain leaves idle"""
-    k = str(device)
+def side_stream(device, index=0):
+    """extra CUDA streams per device: independent kernel chains (connector vs world-model backward, critic vs actor backward,
+    row chunks of the imagination rollout) are enqueued there so their latency-bound small kernels fill the SMs the other chain
+    leaves idle"""
+    k = (str(device), index)
     s = _SIDE_STREAMS.get(k)
     if s is None:
         s = _SIDE_STREAMS[k] = torch.cuda.Stream(device=device)

@@ -1268,6 +1268,12 @@ class PhiloxNoise:
         lib.genrl_fill_normal(_st(), out.data_ptr(), out.numel(), self.seed, self.offset, self.step_counter(device).data_ptr())
         return out
 
+    def randn_into(self, out):
+        """standard-normal fill of a preallocated contiguous fp32 buffer"""
+        self.offset += 1
+        lib.genrl_fill_normal(_st(), out.data_ptr(), out.numel(), self.seed, self.offset, self.step_counter(out.device).data_ptr())
+        return out
+
     def randint(self):
         return None
 
@@ -1296,6 +1302,10 @@ class TapeNoise:
 
     def randn(self, shape, device):
         return self._next("randn").to(device=device, dtype=torch.float32).reshape(shape).contiguous()
+
+    def randn_into(self, out):
+        out.copy_(self._next("randn").to(device=out.device, dtype=torch.float32).reshape(out.shape))
+        return out
 
     def randint(self):
         return self._next("randint")

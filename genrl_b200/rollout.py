@@ -1,0 +1,279 @@
+"""The imagination rollout as ONE autograd node with explicit buffers (reference WorldModel.imagine, agent/dreamer.py:254-287, over
+EnsembleRSSM.img_step dreamer_utils.py:459-487, the actor MLP :718-747 / :814-819 and OneHotDist :177-197).
+
+The op-level path builds the rollout out of ~45 autograd nodes per step: concatenations that materialise [stoch | action], [x | h] and
+[stoch | deter], dtype casts, `torch.stack` of the per-step lists, and — in the backward — autograd's own gradient-accumulation adds.
+Here the H steps run over pre-laid-out buffers:
+
+  feat  [H+1, N, S*K + D]   compute dtype   the categorical sampler writes its one-hot straight into feat[i][:, :S*K], the GRU gate kernel
+                                            writes deter straight into feat[i][:, S*K:]; every consumer GEMM takes (pointer, leading dim)
+  stoch / deter / logit / action [H+1, N, .] fp32   the API's `seq` entries, written in place by the same kernels (no torch.stack)
+  per-step saved tensors (pre-LayerNorm activations, statistics, GRU pre-activations, head outputs, noise) in [H, N, .] slabs
+
+and the backward is the hand-sequenced reverse loop: gradient sums are fused into accumulate-epilogues of the dgrad GEMMs / the linear
+straight-through backward, the actor's weight gradients are ONE GEMM per layer over all H*N rows (the slabs are already contiguous),
+nothing goes through autograd inside the rollout.  20 launches per step forward instead of ~45, no ATen kernels.
+
+Gradients flow out of `feat`, `stoch` and `policy_ent` (the only rollout outputs a GenRL loss reads: dreamer.py:392-438,
+tools/genrl_utils.py:250-277) into the ACTOR's parameters; the world model is frozen inside the behaviour update (dreamer.py:376-384) and
+the start state is detached (dreamer.py:78-79).  Anything else falls back to the op-level path in WorldModel.imagine.
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from ._lib import lib
+from .ops import _st, _p, _ld, _CODE, ACT_SILU, F32
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def supported(policy, rssm):
+    """the explicit rollout covers the GenRL configuration: LayerNorm MLP actor with a 'normal' head, frozen single-member RSSM"""
+    from .agent import dreamer_utils as common
+    if not isinstance(policy, common.MLP) or not isinstance(rssm, common.EnsembleRSSM):
+        return False
+    if policy._norm != "layer" or policy._out._dist != "normal" or not isinstance(policy._act, torch.nn.SiLU):
+        return False
+    if any(p.requires_grad for p in rssm.parameters()):
+        return False
+    if any(p.requires_grad and ops.param_info(p) is None for p in policy.parameters()):
+        return False            # parameter gradients are written straight into the ParamStore's flat buffers
+    return True
+
+
+class _Slab:
+    """[steps, N, cols] buffer in a given dtype whose rows keep a TMA-legal leading dimension"""
+
+    def __init__(self, steps, N, cols, dtype, device, zero=False):
+        ld = _pad8(cols) if dtype == torch.bfloat16 else cols
+        self.t = (torch.zeros if (zero or ld != cols) else torch.empty)(steps, N, ld, device=device, dtype=dtype)
+        self.cols = cols
+
+    def __getitem__(self, i):
+        return self.t[i][:, :self.cols]
+
+    def all(self, lo=0, hi=None):
+        """rows of steps lo..hi-1 as one [steps*N, cols] matrix (contiguous slab)"""
+        hi = self.t.shape[0] if hi is None else hi
+        return self.t[lo:hi].reshape(-1, self.t.shape[2])[:, :self.cols]
+
+
+def _ln_fwd(x, gamma, beta, eps, y, stats):
+    lib.genrl_ln_act_fwd(_st(), _p(x), _ld(x), _p(gamma), _p(beta), float(eps), ACT_SILU, _p(y), _ld(y), _p(stats), x.shape[0], x.shape[1],
+                         _CODE[x.dtype])
+
+
+def _ln_bwd(dy, pre, gamma, beta, stats, dpre):
+    lib.genrl_ln_act_bwd(_st(), _p(dy), _ld(dy), _p(pre), _ld(pre), _p(gamma), _p(beta), _p(stats), ACT_SILU, _p(dpre), _ld(dpre), None, None,
+                         None, pre.shape[0], pre.shape[1], _CODE[pre.dtype])
+
+
+def _copy(src, dst, accumulate=False):
+    lib.genrl_gather_rows(_st(), _p(src), _ld(src), _CODE[src.dtype], None, None, _p(dst), _ld(dst), _CODE[dst.dtype], dst.shape[0], src.shape[1],
+                          int(accumulate))
+
+
+class _Rollout(Function):
+    @staticmethod
+    def forward(ctx, stoch0, deter0, logit0, policy, rssm, horizon, eval_policy, *actor_params):
+        cd = ops.compute_dtype()
+        dev = deter0.device
+        S, K, D, Hd = rssm._stoch, rssm._discrete, rssm._deter, rssm._hidden
+        SK = S * K
+        N = deter0.shape[0]
+        H = horizon
+        L, U, A = policy._layers, policy._units, int(policy._out._out.weight.shape[0])
+        noise = ops.noise
+        # ---- weights in compute layout -----------------------------------------------------------------------------------------------------
+        W = ops.compute_weight
+        dense = [getattr(policy, f"dense{l}") for l in range(L)]
+        norms = [getattr(policy, f"norm{l}")._layer for l in range(L)]
+        w_head = torch.cat([W(policy._out._out.weight), W(policy._out._std.weight)], 0).contiguous()            # [2A, U]
+        b_head = torch.cat([policy._out._out.bias.detach(), policy._out._std.bias.detach()], 0).contiguous()
+        lin_in, ln_in = rssm._img_in[0], rssm._img_in[1]._layer
+        lin_out, ln_out = rssm._ensemble_img_out[0][0], rssm._ensemble_img_out[0][1]._layer
+        lin_dist = rssm._ensemble_img_dist[0]
+        w_gru, ln_gru = rssm._cell._layer.weight, rssm._cell._norm
+        # ---- buffers -----------------------------------------------------------------------------------------------------------------------
+        feat = _Slab(H + 1, N, SK + D, cd, dev)
+        stoch = torch.empty(H + 1, N, SK, device=dev, dtype=torch.float32)
+        deter = torch.empty(H + 1, N, D, device=dev, dtype=torch.float32)
+        logit = torch.empty(H + 1, N, SK, device=dev, dtype=torch.float32)
+        action = torch.zeros(H + 1, N, A, device=dev, dtype=torch.float32)
+        ent = torch.empty(max(H, 1), N, device=dev, dtype=torch.float32)
+        a_pre = [_Slab(H, N, U, cd, dev) for _ in range(L)]
+        a_y = [_Slab(H, N, U, cd, dev) for _ in range(L)]
+        a_st = [torch.empty(H, N, 2, device=dev, dtype=torch.float32) for _ in range(L)]
+        out2 = torch.empty(H, N, 2 * A, device=dev, dtype=torch.float32)
+        eps = torch.empty(H, N, A, device=dev, dtype=torch.float32)
+        in_pre, in_st = _Slab(H, N, Hd, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
+        z, g_st = _Slab(H, N, 3 * D, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
+        out_pre, out_st = _Slab(H, N, Hd, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
+        xin = _Slab(1, N, SK + A, cd, dev, zero=True)[0]             # [stoch_{i-1} | action_i]
+        xh = _Slab(1, N, Hd + D, cd, dev)[0]                        # [x | deter_{i-1}]
+        y_out = _Slab(1, N, Hd, cd, dev)[0]
+        # ---- step 0 = the start state ------------------------------------------------------------------------------------------------------
+        stoch[0].copy_(stoch0.reshape(N, SK))
+        deter[0].copy_(deter0)
+        logit[0].copy_(logit0.reshape(N, SK))
+        _copy(stoch[0], feat[0][:, :SK]); _copy(deter[0], feat[0][:, SK:])
+        _copy(stoch[0], xin[:, :SK]); _copy(deter[0], xh[:, Hd:])
+        if not isinstance(noise, ops.PhiloxNoise):       # dreamer.py:259-260 samples (and discards) one action at the start state: keep the
+            noise.randn_into(torch.empty(N, A, device=dev, dtype=torch.float32))      # replayed reference draws in step
+        step_ptr = ops.noise_step_ptr(dev)
+        for i in range(1, H + 1):
+            j = i - 1
+            # actor on sg(feat_{i-1})                                                                     dreamer.py:265-266, dreamer_utils.py:738-747
+            x = feat[j]
+            for l in range(L):
+                ops.gemm(x, W(dense[l].weight), out=a_pre[l][j], bias=dense[l].bias.detach() if dense[l].bias is not None else None)
+                _ln_fwd(a_pre[l][j], norms[l].weight, norms[l].bias, norms[l].eps, a_y[l][j], a_st[l][j])
+                x = a_y[l][j]
+            ops.gemm(x, w_head, out=out2[j], bias=b_head)
+            e = None
+            if not eval_policy:
+                e = noise.randn_into(eps[j])
+            lib.genrl_actor_head_fwd(_st(), _p(out2[j]), 2 * A, _p(e), int(bool(eval_policy)), _p(action[i]), A, _p(xin[:, SK:]), _ld(xin), _p(ent[j]),
+                                     N, A, _CODE[cd])
+            # img_step                                                                                     dreamer_utils.py:459-487
+            ops.gemm(xin, W(lin_in.weight), out=in_pre[j], bias=lin_in.bias.detach())
+            _ln_fwd(in_pre[j], ln_in.weight, ln_in.bias, ln_in.eps, xh[:, :Hd], in_st[j])
+            ops.gemm(xh, W(w_gru), out=z[j])
+            lib.genrl_gru_fwd(_st(), _p(z[j]), _ld(z[j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(deter[j]), D, _p(deter[i]), D,
+                              _p(feat[i][:, SK:]), _ld(feat[i]), _p(g_st[j]), N, D, _CODE[cd])
+            ops.gemm(feat[i][:, SK:], W(lin_out.weight), out=out_pre[j], bias=lin_out.bias.detach())
+            _ln_fwd(out_pre[j], ln_out.weight, ln_out.bias, ln_out.eps, y_out, out_st[j])
+            ops.gemm(y_out, W(lin_dist.weight), out=logit[i], bias=lin_dist.bias.detach())
+            noise.randint()
+            nz, seed, off = noise.exp(N * S, K, dev)
+            lib.genrl_cat_sample_fwd(_st(), _p(logit[i]), _p(nz), seed, off, step_ptr if nz is None else None, 1, _p(feat[i][:, :SK]), _ld(feat[i]),
+                                     _p(stoch[i]), SK, None, N, S, K, _CODE[cd])
+            if i < H:
+                _copy(feat[i][:, :SK], xin[:, :SK]); _copy(feat[i][:, SK:], xh[:, Hd:])
+        feat_out = feat.t[:, :, :SK + D]
+        ctx.mods = (policy, rssm, dense, norms, w_head)
+        ctx.dims = (S, K, D, Hd, N, H, L, U, A, cd, bool(eval_policy))
+        ctx.bufs = dict(feat=feat, deter=deter, logit=logit, a_pre=a_pre, a_y=a_y, a_st=a_st, out2=out2, eps=eps, in_pre=in_pre, in_st=in_st, z=z,
+                        g_st=g_st, out_pre=out_pre, out_st=out_st)
+        ctx.n_params = len(actor_params)
+        stoch_v, logit_v = stoch.reshape(H + 1, N, S, K), logit.reshape(H + 1, N, S, K)
+        ctx.mark_non_differentiable(deter, logit_v, action)
+        return feat_out, stoch_v, deter, logit_v, action, (ent if H > 0 else ent[:0])
+
+    @staticmethod
+    def backward(ctx, dfeat, dstoch, _ddeter, _dlogit, _daction, dent):
+        policy, rssm, dense, norms, w_head = ctx.mods
+        S, K, D, Hd, N, H, L, U, A, cd, eval_policy = ctx.dims
+        b = ctx.bufs
+        SK = S * K
+        dev = b["deter"].device
+        W = ops.compute_weight
+        with ops.use_dtype(cd):
+            lin_in, ln_in = rssm._img_in[0], rssm._img_in[1]._layer
+            lin_out, ln_out = rssm._ensemble_img_out[0][0], rssm._ensemble_img_out[0][1]._layer
+            lin_dist = rssm._ensemble_img_dist[0]
+            w_gru_c, ln_gru = W(rssm._cell._layer.weight), rssm._cell._norm
+            if dfeat is not None:
+                dfeat = dfeat if (dfeat.dtype == cd and dfeat.stride(-1) == 1) else dfeat.to(cd).contiguous()
+            if dstoch is not None:
+                dstoch = dstoch.reshape(H + 1, N, SK)
+                dstoch = dstoch if dstoch.stride(-1) == 1 else dstoch.contiguous()
+            if dent is not None:
+                dent = dent.contiguous().float()
+            # slabs the deferred parameter gradients read after the loop
+            a_dy = [_Slab(H, N, U, cd, dev) for _ in range(L)]
+            a_dpre = [_Slab(H, N, U, cd, dev) for _ in range(L)]
+            dout2c = _Slab(H, N, 2 * A, cd, dev, zero=True)
+            dout2 = torch.empty(N, 2 * A, device=dev, dtype=torch.float32)
+            G = [torch.zeros(N, D, device=dev, dtype=torch.float32), torch.empty(N, D, device=dev, dtype=torch.float32)]     # d loss / d deter_i
+            dlogit = torch.empty(N, SK, device=dev, dtype=torch.float32)
+            dlogit_c = dlogit if cd == torch.float32 else _Slab(1, N, SK, cd, dev)[0]
+            dy_out = _Slab(1, N, Hd, cd, dev)[0]
+            dpre_out = _Slab(1, N, Hd, cd, dev)[0]
+            dz = _Slab(1, N, 3 * D, cd, dev)[0]
+            dx = _Slab(1, N, Hd, cd, dev)[0]
+            dpre_in = _Slab(1, N, Hd, cd, dev)[0]
+            dxin = [_Slab(1, N, SK + A, cd, dev)[0], _Slab(1, N, SK + A, cd, dev)[0]]
+            have_carry = False
+            cur = 0
+            for i in range(H, 0, -1):
+                j = i - 1
+                # ---- d/d stoch_i : feat slice + explicit stoch output + the next step's input projection ------------------------------------
+                srcs = []
+                if dfeat is not None:
+                    srcs.append(dfeat[i][:, :SK])
+                if dstoch is not None:
+                    srcs.append(dstoch[i])
+                if have_carry:
+                    srcs.append(dxin[1 - cur][:, :SK])
+                gh = G[cur]
+                if dfeat is not None:
+                    _copy(dfeat[i][:, SK:], gh, accumulate=True)
+                if srcs:
+                    for n_, s_ in enumerate(srcs):          # the straight-through backward is linear in d stoch: accumulate the contributions
+                        lib.genrl_cat_sample_bwd(_st(), _p(b["logit"][i]), _p(s_), _ld(s_), 1, _p(dlogit), int(n_ > 0), N, S, K, _CODE[s_.dtype])
+                    if dlogit_c is not dlogit:
+                        _copy(dlogit, dlogit_c)
+                    ops.gemm(dlogit_c, W(lin_dist.weight), out=dy_out, trans_w=True)
+                    _ln_bwd(dy_out, b["out_pre"][j], ln_out.weight, ln_out.bias, b["out_st"][j], dpre_out)
+                    ops.gemm(dpre_out, W(lin_out.weight), out=gh, trans_w=True, accumulate=True)
+                # ---- GRU cell -------------------------------------------------------------------------------------------------------------
+                gn = G[1 - cur]
+                lib.genrl_gru_bwd(_st(), _p(gh), D, _p(b["z"][j]), _ld(b["z"][j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D,
+                                  _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D, None, None, N, D, _CODE[cd])
+                ops.gemm(dz, w_gru_c[:, :Hd], out=dx, trans_w=True)
+                if i > 1:
+                    ops.gemm(dz, w_gru_c[:, Hd:], out=gn, trans_w=True, accumulate=True)
+                _ln_bwd(dx, b["in_pre"][j], ln_in.weight, ln_in.bias, b["in_st"][j], dpre_in)
+                ops.gemm(dpre_in, W(lin_in.weight), out=dxin[cur], trans_w=True)
+                # ---- actor head and trunk (input is sg(feat_{i-1}): no gradient leaves through it) --------------------------------------------
+                e = None if eval_policy else b["eps"][j]
+                if e is None:
+                    e = torch.zeros(N, A, device=dev, dtype=torch.float32)
+                de = None if dent is None else dent[j]
+                lib.genrl_actor_head_bwd(_st(), _p(b["out2"][j]), 2 * A, _p(e), _p(dxin[cur][:, SK:]), _ld(dxin[cur]), _p(de),
+                                         1.0 if de is not None else 0.0, _p(dout2), 2 * A, N, A, _CODE[cd])
+                _copy(dout2, dout2c[j])
+                ops.gemm(dout2c[j], w_head, out=a_dy[L - 1][j], trans_w=True)
+                for l in range(L - 1, -1, -1):
+                    _ln_bwd(a_dy[l][j], b["a_pre"][l][j], norms[l].weight, norms[l].bias, b["a_st"][l][j], a_dpre[l][j])
+                    if l > 0:
+                        ops.gemm(a_dpre[l][j], W(dense[l].weight), out=a_dy[l - 1][j], trans_w=True)
+                have_carry = True
+                cur = 1 - cur
+            # ---- actor parameter gradients: one GEMM / one column pass per layer over all H*N rows --------------------------------------------
+            if H > 0 and dense[0].weight.requires_grad:
+                st = _st()
+                for l in range(L):
+                    X = b["feat"].all(0, H) if l == 0 else b["a_y"][l - 1].all()
+                    DP, DY, PRE = a_dpre[l].all(), a_dy[l].all(), b["a_pre"][l].all()
+                    gbuf, _ = ops._grad_buf(dense[l].weight)
+                    ops.gemm(DP, X, out=gbuf.view(U, -1), trans_a=True, trans_w=True, accumulate=True)
+                    gb, _ = ops._grad_buf(norms[l].weight)
+                    bb, _ = ops._grad_buf(norms[l].bias)
+                    lb = ops._grad_buf(dense[l].bias)[0] if dense[l].bias is not None else None
+                    lib.genrl_ln_colgrad(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(DP), _ld(DP), _p(norms[l].weight), _p(norms[l].bias),
+                                         _p(b["a_st"][l].reshape(-1, 2)), ACT_SILU, _p(gb), _p(bb), _p(lb), DP.shape[0], U, _CODE[cd])
+                XH = b["a_y"][L - 1].all()
+                DO = dout2c.all()
+                for part, lin in ((0, policy._out._out), (1, policy._out._std)):
+                    gbuf, _ = ops._grad_buf(lin.weight)
+                    dsl = DO[:, part * A:(part + 1) * A]
+                    ops.gemm(dsl, XH, out=gbuf.view(A, U), trans_a=True, trans_w=True, accumulate=True)
+                    bbuf, _ = ops._grad_buf(lin.bias)
+                    lib.genrl_colsum(st, _p(dsl), _ld(dsl), _p(bbuf), dsl.shape[0], A, _CODE[cd])
+        return (None,) * (7 + ctx.n_params)
+
+
+def imagine_rows(policy, rssm, start, horizon, eval_policy=False):
+    """start: dict of flattened rows {stoch [N,S,K], deter [N,D], logit [N,S,K]} -> seq dict with [H+1, N, ...] entries"""
+    params = list(policy.parameters())
+    feat, stoch, deter, logit, action, ent = _Rollout.apply(start["stoch"].detach(), start["deter"].detach(), start["logit"].detach(), policy, rssm,
+                                                           int(horizon), bool(eval_policy), *params)
+    seq = {"stoch": stoch, "deter": deter, "logit": logit, "feat": feat, "action": action}
+    if not eval_policy and horizon > 0:
+        seq["policy_ent"] = ent
+    return seq

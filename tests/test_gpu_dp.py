@@ -40,6 +40,10 @@ class RecordedNoise:
     def randn(self, shape, device):
         return self._take(tuple(shape), device, "randn")
 
+    def randn_into(self, out):
+        out.copy_(self._take(tuple(out.shape), out.device, "randn"))
+        return out
+
     def randint(self):
         return None
 
