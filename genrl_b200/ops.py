@@ -358,11 +358,38 @@ def ln_act(x, gamma, beta, eps=1e-5, act=ACT_SILU):
 # graph): N = 128 / 512 fused 10.5 / 13.9 us vs 12.7 / 15.9 us unfused; at N = 1024 (cluster of 8) the un-overlapped epilogue + two
 # cluster barriers cost as much as the separate LayerNorm launch (20.2 vs 19.5 us), so the 1024-wide layers stay on the two-kernel path.
 FUSED_LN_MAX_N = 512
+CHAIN_MIN_ROWS = 64            # below that a 128-row stripe is mostly padding
 
 
 def fused_linear_ln_enabled():
     import os
     return os.environ.get("GENRL_FUSED_LN", "1") != "0"
+
+
+def chain_supported(N, dtype=None):
+    """the persistent cluster chain kernel (csrc/mlp_chain.cu): bf16, layer width a multiple of 256 up to 1024"""
+    import os
+    dtype = dtype or _State.dtype
+    return dtype == torch.bfloat16 and N % 256 == 0 and 256 <= N <= 1024 and os.environ.get("GENRL_CHAIN", "1") != "0"
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(q) if q else 0) for q in ptrs])
+
+
+def mlp_chain_fwd(x, weights, biases, gammas, betas, eps, act, pre, y, stats):
+    """y_l = act(LN(y_{l-1} W_l^T + b_l)) for l = 0..L-1 in one launch.  x [M, K0] bf16; weights: compute-layout bf16 [N, K_l]; pre / y: lists of
+    [M, N] bf16 output views sharing one leading dimension each; stats: list of [M, 2] fp32."""
+    L = len(weights)
+    M, K0 = x.shape
+    N = weights[0].shape[0]
+    ldw = (ctypes.c_longlong * L)(*[_ld(w) for w in weights])
+    ldpre, ldy = _ld(pre[0]), _ld(y[0])
+    assert all(_ld(t) == ldpre for t in pre) and all(_ld(t) == ldy for t in y)
+    lib.genrl_mlp_chain_fwd(_st(), M, N, L, _p(x), _ld(x), K0, _ptr_array([_p(w) for w in weights]), ldw,
+                            _ptr_array([_p(b) for b in biases]), _ptr_array([_p(g) for g in gammas]), _ptr_array([_p(b) for b in betas]),
+                            float(eps), int(act), _ptr_array([_p(t) for t in pre]), ldpre, _ptr_array([_p(t) for t in y]), ldy,
+                            _ptr_array([_p(t) for t in stats]))
 
 
 class _LinearLnAct(Function):
@@ -383,6 +410,19 @@ class _LinearLnAct(Function):
             stats = torch.empty(M, 2, device=x.device, dtype=torch.float32)
             lib.genrl_gemm_ln_fwd(_st(), M, N, x.shape[1], _p(x), _ld(x), _p(wc), _ld(wc), _p(b.detach() if b is not None else None),
                                   _p(gamma.detach()), _p(beta.detach()), float(eps), act, _p(pre), _ld(pre), _p(y), _ld(y), _p(stats))
+            ctx.save_for_backward(x, pre, stats)
+            ctx.w, ctx.b, ctx.gamma, ctx.beta, ctx.act = w, b, gamma, beta, act
+            return y
+        if chain_supported(N) and N > FUSED_LN_MAX_N and x.shape[0] >= CHAIN_MIN_ROWS:
+            # one persistent cluster launch: GEMM + bias + LayerNorm + SiLU (clusters of N/256 CTAs, csrc/mlp_chain.cu)
+            wc = compute_weight(w)
+            if _ld(x) % 8 or x.data_ptr() % 16:
+                x = cast_to(x, torch.bfloat16)
+            M = x.shape[0]
+            pre = empty_act(M, N, x.device)
+            y = empty_act(M, N, x.device)
+            stats = torch.empty(M, 2, device=x.device, dtype=torch.float32)
+            mlp_chain_fwd(x, [wc], [b.detach() if b is not None else None], [gamma.detach()], [beta.detach()], eps, act, [pre], [y], [stats])
             ctx.save_for_backward(x, pre, stats)
             ctx.w, ctx.b, ctx.gamma, ctx.beta, ctx.act = w, b, gamma, beta, act
             return y

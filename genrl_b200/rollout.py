@@ -79,6 +79,7 @@ def _copy(src, dst, accumulate=False):
 class _Rollout(Function):
     @staticmethod
     def forward(ctx, stoch0, deter0, logit0, policy, rssm, horizon, eval_policy, *actor_params):
+        ctx.set_materialize_grads(False)       # unused outputs (stoch with the env reward, ...) arrive as None, not as zero slabs
         cd = ops.compute_dtype()
         dev = deter0.device
         S, K, D, Hd = rssm._stoch, rssm._discrete, rssm._deter, rssm._hidden
@@ -124,14 +125,24 @@ class _Rollout(Function):
         if not isinstance(noise, ops.PhiloxNoise):       # dreamer.py:259-260 samples (and discards) one action at the start state: keep the
             noise.randn_into(torch.empty(N, A, device=dev, dtype=torch.float32))      # replayed reference draws in step
         step_ptr = ops.noise_step_ptr(dev)
+        big = N >= ops.CHAIN_MIN_ROWS
+        chain_a = big and ops.chain_supported(U, cd) and all(n.eps == norms[0].eps for n in norms) and (SK + D) % 8 == 0
+        chain_h = big and ops.chain_supported(Hd, cd) and (SK + D) % 8 == 0 and SK % 8 == 0
         for i in range(1, H + 1):
             j = i - 1
             # actor on sg(feat_{i-1})                                                                     dreamer.py:265-266, dreamer_utils.py:738-747
             x = feat[j]
-            for l in range(L):
-                ops.gemm(x, W(dense[l].weight), out=a_pre[l][j], bias=dense[l].bias.detach() if dense[l].bias is not None else None)
-                _ln_fwd(a_pre[l][j], norms[l].weight, norms[l].bias, norms[l].eps, a_y[l][j], a_st[l][j])
-                x = a_y[l][j]
+            if chain_a:
+                # the whole trunk in one persistent cluster launch (csrc/mlp_chain.cu)
+                ops.mlp_chain_fwd(x, [W(d.weight) for d in dense], [d.bias.detach() if d.bias is not None else None for d in dense],
+                                  [n.weight for n in norms], [n.bias for n in norms], norms[0].eps, ACT_SILU,
+                                  [a_pre[l][j] for l in range(L)], [a_y[l][j] for l in range(L)], [a_st[l][j] for l in range(L)])
+                x = a_y[L - 1][j]
+            else:
+                for l in range(L):
+                    ops.gemm(x, W(dense[l].weight), out=a_pre[l][j], bias=dense[l].bias.detach() if dense[l].bias is not None else None)
+                    _ln_fwd(a_pre[l][j], norms[l].weight, norms[l].bias, norms[l].eps, a_y[l][j], a_st[l][j])
+                    x = a_y[l][j]
             ops.gemm(x, w_head, out=out2[j], bias=b_head)
             e = None
             if not eval_policy:
@@ -139,13 +150,21 @@ class _Rollout(Function):
             lib.genrl_actor_head_fwd(_st(), _p(out2[j]), 2 * A, _p(e), int(bool(eval_policy)), _p(action[i]), A, _p(xin[:, SK:]), _ld(xin), _p(ent[j]),
                                      N, A, _CODE[cd])
             # img_step                                                                                     dreamer_utils.py:459-487
-            ops.gemm(xin, W(lin_in.weight), out=in_pre[j], bias=lin_in.bias.detach())
-            _ln_fwd(in_pre[j], ln_in.weight, ln_in.bias, ln_in.eps, xh[:, :Hd], in_st[j])
+            if chain_h:
+                ops.mlp_chain_fwd(xin, [W(lin_in.weight)], [lin_in.bias.detach()], [ln_in.weight], [ln_in.bias], ln_in.eps, ACT_SILU,
+                                  [in_pre[j]], [xh[:, :Hd]], [in_st[j]])
+            else:
+                ops.gemm(xin, W(lin_in.weight), out=in_pre[j], bias=lin_in.bias.detach())
+                _ln_fwd(in_pre[j], ln_in.weight, ln_in.bias, ln_in.eps, xh[:, :Hd], in_st[j])
             ops.gemm(xh, W(w_gru), out=z[j])
             lib.genrl_gru_fwd(_st(), _p(z[j]), _ld(z[j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(deter[j]), D, _p(deter[i]), D,
                               _p(feat[i][:, SK:]), _ld(feat[i]), _p(g_st[j]), N, D, _CODE[cd])
-            ops.gemm(feat[i][:, SK:], W(lin_out.weight), out=out_pre[j], bias=lin_out.bias.detach())
-            _ln_fwd(out_pre[j], ln_out.weight, ln_out.bias, ln_out.eps, y_out, out_st[j])
+            if chain_h:
+                ops.mlp_chain_fwd(feat[i][:, SK:], [W(lin_out.weight)], [lin_out.bias.detach()], [ln_out.weight], [ln_out.bias], ln_out.eps, ACT_SILU,
+                                  [out_pre[j]], [y_out], [out_st[j]])
+            else:
+                ops.gemm(feat[i][:, SK:], W(lin_out.weight), out=out_pre[j], bias=lin_out.bias.detach())
+                _ln_fwd(out_pre[j], ln_out.weight, ln_out.bias, ln_out.eps, y_out, out_st[j])
             ops.gemm(y_out, W(lin_dist.weight), out=logit[i], bias=lin_dist.bias.detach())
             noise.randint()
             nz, seed, off = noise.exp(N * S, K, dev)

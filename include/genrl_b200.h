@@ -35,6 +35,13 @@ int genrl_gemm_ln_fwd(void* stream, int M, int N, int K, const void* A, long lon
                       const float* gamma, const float* beta, float eps, int act, void* pre, long long ldpre, void* y, long long ldy,
                       float* stats);
 
+/* Chain of L layers y_l = act(LayerNorm(y_{l-1} W_l^T + b_l)) in ONE persistent cluster kernel (bf16, N = 256/512/768/1024; K_0 free, K_l = N):
+ * MLP trunks (dreamer_utils.py:718-747) and the single Linear+NormLayer+SiLU blocks of the RSSM (:339-346).  W / bias / gamma / beta / pre / y /
+ * stats are host arrays of L device pointers; pre_l (pre-LayerNorm values) and stats_l = (mean, rstd) per row are kept for the backward. */
+int genrl_mlp_chain_fwd(void* stream, int M, int N, int L, const void* x, long long ldx, int K0, const void* const* W, const long long* ldw,
+                        const float* const* bias, const float* const* gamma, const float* const* beta, float eps, int act,
+                        void* const* pre, long long ldpre, void* const* y, long long ldy, float* const* stats);
+
 /* LayerNorm(+SiLU) rows: NormLayer dreamer_utils.py:844-859 / ImgChLayerNorm :1031-1040 + act (:744, :589). */
 int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act, void* y,
                      long long ldy, float* stats, long long M, int D, int dtype);

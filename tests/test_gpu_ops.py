@@ -547,3 +547,31 @@ def test_vlm_reward_alignment_and_gradient(dtype, T, N, E, align):
     assert (reward.cpu() - ref.detach()).abs().max() <= tol
     gscale = float(pa_r.grad.abs().max())
     assert (pa_d.grad.float().cpu() - pa_r.grad).abs().max() <= tol * gscale + (1e-6 if dtype == torch.float32 else 1e-2 * gscale)
+
+
+@pytest.mark.parametrize("M,K0,N,L", [(2400, 2048, 1024, 4), (300, 1034, 1024, 1), (128, 256, 256, 3), (5000, 512, 512, 2), (77, 1024, 768, 2)])
+def test_mlp_chain_fwd_matches_layerwise_reference(M, K0, N, L):
+    """persistent cluster chain kernel (csrc/mlp_chain.cu) vs fp32 torch on the same bf16 operands, layer by layer: pre-activations,
+    (mean, rstd), activations; each layer's reference consumes the KERNEL's previous activation so that errors do not compound"""
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K0, generator=g)).to(DEV, torch.bfloat16)
+    Ws = [(torch.randn(N, K0 if l == 0 else N, generator=g) / math.sqrt(K0 if l == 0 else N)).to(DEV, torch.bfloat16) for l in range(L)]
+    bs = [(torch.randn(N, generator=g) * 0.1).to(DEV) for _ in range(L)]
+    gs = [(1 + 0.1 * torch.randn(N, generator=g)).to(DEV) for _ in range(L)]
+    bt = [(0.1 * torch.randn(N, generator=g)).to(DEV) for _ in range(L)]
+    slab = lambda: [torch.empty(M, N + 8, device=DEV, dtype=torch.bfloat16)[:, :N] for _ in range(L)]
+    pre, y = slab(), slab()
+    stats = [torch.empty(M, 2, device=DEV) for _ in range(L)]
+    with ops.use_dtype(torch.bfloat16):
+        ops.mlp_chain_fwd(x, Ws, bs, gs, bt, 1e-5, ops.ACT_SILU, pre, y, stats)
+    torch.cuda.synchronize()
+    inp = x
+    for l in range(L):
+        ref_pre = inp.float() @ Ws[l].float().t() + bs[l]
+        close(pre[l], ref_pre, rtol=1e-2, atol=2e-2, msg=f"layer {l} pre")
+        mean, var = ref_pre.mean(-1), ref_pre.var(-1, unbiased=False)
+        close(stats[l][:, 0], mean, rtol=1e-3, atol=1e-3, msg=f"layer {l} mean")
+        close(stats[l][:, 1], 1 / torch.sqrt(var + 1e-5), rtol=2e-3, atol=1e-4, msg=f"layer {l} rstd")
+        ref_y = F.silu(F.layer_norm(ref_pre, (N,), gs[l], bt[l], 1e-5))
+        close(y[l], ref_y, rtol=1e-2, atol=2e-2, msg=f"layer {l} y")
+        inp = y[l]
