@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
-    ap.add_argument("--rollout-streams", type=int, default=2, help="row chunks of the imagination rollout enqueued on separate CUDA streams")
+    ap.add_argument("--rollout-streams", type=int, default=1, help="row chunks of the imagination rollout enqueued on separate CUDA streams (measured: 2-4 chunks are 9-11 % slower, profiles/r02_notes.md)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: fp16 autocast (the reference's precision: 16)")
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: sample size in sequences (default REF_SAMPLE_B)")

@@ -359,6 +359,9 @@ def ln_act(x, gamma, beta, eps=1e-5, act=ACT_SILU):
 # cluster barriers cost as much as the separate LayerNorm launch (20.2 vs 19.5 us), so the 1024-wide layers stay on the two-kernel path.
 FUSED_LN_MAX_N = 512
 CHAIN_MIN_ROWS = 64            # below that a 128-row stripe is mostly padding
+# Measured on B200 (tools/chain_bench.py, profiles/r02_notes.md): at 36 000-38 400 rows the chain kernel's un-overlapped epilogue loses to the
+# double-buffered persistent 256x128 GEMM + row LayerNorm (188 vs 140 us per 1024-wide layer); it pays at the rollout's 2 400 rows.
+CHAIN_MAX_ROWS = int(__import__("os").environ.get("GENRL_CHAIN_MAX_ROWS", "8192"))
 
 
 def fused_linear_ln_enabled():
@@ -413,7 +416,7 @@ class _LinearLnAct(Function):
             ctx.save_for_backward(x, pre, stats)
             ctx.w, ctx.b, ctx.gamma, ctx.beta, ctx.act = w, b, gamma, beta, act
             return y
-        if chain_supported(N) and N > FUSED_LN_MAX_N and x.shape[0] >= CHAIN_MIN_ROWS:
+        if chain_supported(N) and N > FUSED_LN_MAX_N and CHAIN_MIN_ROWS <= x.shape[0] <= CHAIN_MAX_ROWS:
             # one persistent cluster launch: GEMM + bias + LayerNorm + SiLU (clusters of N/256 CTAs, csrc/mlp_chain.cu)
             wc = compute_weight(w)
             if _ld(x) % 8 or x.data_ptr() % 16:

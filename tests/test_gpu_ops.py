@@ -554,8 +554,9 @@ def test_mlp_chain_fwd_matches_layerwise_reference(M, K0, N, L):
     """persistent cluster chain kernel (csrc/mlp_chain.cu) vs fp32 torch on the same bf16 operands, layer by layer: pre-activations,
     (mean, rstd), activations; each layer's reference consumes the KERNEL's previous activation so that errors do not compound"""
     g = torch.Generator().manual_seed(M + N)
-    x = (torch.randn(M, K0, generator=g)).to(DEV, torch.bfloat16)
-    Ws = [(torch.randn(N, K0 if l == 0 else N, generator=g) / math.sqrt(K0 if l == 0 else N)).to(DEV, torch.bfloat16) for l in range(L)]
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 8))[:, :t.shape[1]]          # TMA-legal leading dimension
+    x = pad((torch.randn(M, K0, generator=g)).to(DEV, torch.bfloat16))
+    Ws = [pad((torch.randn(N, K0 if l == 0 else N, generator=g) / math.sqrt(K0 if l == 0 else N)).to(DEV, torch.bfloat16)) for l in range(L)]
     bs = [(torch.randn(N, generator=g) * 0.1).to(DEV) for _ in range(L)]
     gs = [(1 + 0.1 * torch.randn(N, generator=g)).to(DEV) for _ in range(L)]
     bt = [(0.1 * torch.randn(N, generator=g)).to(DEV) for _ in range(L)]
