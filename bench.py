@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total sequences, split evenly over the ranks (default: --batch per rank, weak scaling)")
     ap.add_argument("--rollout-streams", type=int, default=1, help="row chunks of the imagination rollout enqueued on separate CUDA streams (measured: 2-4 chunks are 9-11 % slower, profiles/r02_notes.md)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: fp16 autocast (the reference's precision: 16)")
@@ -190,6 +191,9 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.global_batch:
+        assert args.global_batch % world == 0, f"--global-batch {args.global_batch} does not divide over {world} ranks"
+        args.batch = args.global_batch // world
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native arm) needs a CUDA device: the genrl_b200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -321,7 +325,8 @@ def run_native(args):
 
     frames = world * args.batch * args.length
     line = {"metric": "seq_frames_per_s_full_genrl_update", "value": frames / (ms_step * 1e-3), "unit": "seq-frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == 16 else "f32", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "seq-frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h_bytes, "pipeline": "pinned host batch i+1 copied on a second stream while step i runs; loss of every step read back"},
