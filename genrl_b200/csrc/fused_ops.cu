@@ -431,6 +431,40 @@ __global__ void __launch_bounds__(128) cat_sample_bwd_thr_kernel(const float* __
   }
 }
 
+// rollout backward: two gradient contributions (the feat slice of step i and the next step's input projection) summed on the fly, the logit
+// gradient written in the activation dtype so that it is the dgrad GEMM's A operand as is (no accumulate pass, no cast pass)
+template <typename T>
+__global__ void __launch_bounds__(128) cat_sample_bwd2_thr_kernel(const float* __restrict__ logit, const T* __restrict__ ds1, long long ld1,
+                                                                  const T* __restrict__ ds2, long long ld2, T* __restrict__ dl_out, long long ld_dl,
+                                                                  long long rows, int S) {
+  genrl::pdl_sync();
+  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (g >= rows * S) return;
+  float p[CK], pi[CK], usum, dpi[CK], dl[CK];
+  cat_probs_thr(logit + g * CK, p, pi, usum);
+  const long long row = g / S; const int sidx = (int)(g % S);
+#pragma unroll
+  for (int i = 0; i < CK / 8; ++i) {
+    float v8[8];
+    V8<T>::load(ds1 + row * ld1 + sidx * CK + 8 * i, v8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dpi[8 * i + e] = v8[e];
+    if (ds2) {
+      V8<T>::load(ds2 + row * ld2 + sidx * CK + 8 * i, v8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dpi[8 * i + e] += v8[e];
+    }
+  }
+  cat_probs_bwd_thr(p, pi, usum, dpi, dl);
+#pragma unroll
+  for (int i = 0; i < CK / 8; ++i) {
+    float v8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v8[e] = dl[8 * i + e];
+    V8<T>::store(dl_out + row * ld_dl + sidx * CK + 8 * i, v8);
+  }
+}
+
 // S == 32, K == 32: one warp per row, one latent per lane
 __global__ void __launch_bounds__(128) kl_fwd_thr_kernel(const float* __restrict__ lhs, const float* __restrict__ rhs, float free_bits,
                                                          float* __restrict__ value, float* __restrict__ out, long long rows) {
@@ -677,8 +711,8 @@ __global__ void actor_head_fwd_kernel(const float* __restrict__ out, long long l
 
 template <typename T>
 __global__ void actor_head_bwd_kernel(const float* __restrict__ out, long long ldo, const float* __restrict__ eps, const T* __restrict__ daction,
-                                      long long ldda, const float* __restrict__ dent, float dent_scale, float* __restrict__ dout, long long lddo,
-                                      long long rows, int A) {
+                                      long long ldda, const float* __restrict__ dent, float dent_scale, void* __restrict__ dout, long long lddo,
+                                      int dout_dtype, long long rows, int A) {
   genrl::pdl_sync();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
@@ -689,8 +723,8 @@ __global__ void actor_head_bwd_kernel(const float* __restrict__ out, long long l
     float std = 0.9f * sg + 0.1f;
     float da = daction ? to_f32(daction[i * ldda + a]) : 0.f;
     float dstd = da * eps[i * A + a] + de / std;
-    dout[i * lddo + a] = da * (1.0f - mean * mean);
-    dout[i * lddo + A + a] = dstd * 0.9f * sg * (1.0f - sg);
+    st_any(dout, dout_dtype, (size_t)(i * lddo + a), da * (1.0f - mean * mean));
+    st_any(dout, dout_dtype, (size_t)(i * lddo + A + a), dstd * 0.9f * sg * (1.0f - sg));
   }
 }
 
@@ -1019,6 +1053,18 @@ extern "C" int genrl_cat_sample_bwd(void* stream, const float* logit, const void
   return check_launch("cat_sample_bwd");
 }
 
+// sampled one-hot (K = 32), straight-through backward of ds1 + ds2 (ds2 may be NULL), output in the same dtype as the inputs
+extern "C" int genrl_cat_sample_bwd2(void* stream, const float* logit, const void* ds1, long long ld1, const void* ds2, long long ld2, void* dlogit,
+                                     long long ld_dl, long long rows, int S, int K, int dtype) {
+  if (rows <= 0) return 0;
+  GENRL_REQUIRE(K == CK && f32_vec_ok(logit), "cat_sample_bwd2: K must be %d and logit 16-byte aligned", CK);
+  DISPATCH_T(dtype, {
+    GENRL_REQUIRE(vec_ok<T>(ds1, ld1) && (!ds2 || vec_ok<T>(ds2, ld2)) && vec_ok<T>(dlogit, ld_dl), "cat_sample_bwd2: operands must be 16-byte aligned");
+    genrl::launch_pdl(cat_sample_bwd2_thr_kernel<T>, ceil_div(rows * S, 128), 128, 0, ST(stream), logit, (const T*)ds1, ld1, (const T*)ds2, ld2, (T*)dlogit, ld_dl, rows, S);
+  });
+  return check_launch("cat_sample_bwd2");
+}
+
 extern "C" int genrl_kl_fwd(void* stream, const float* lhs, const float* rhs, float free_bits, float* value, float* out4, long long rows, int S, int K) {
   if (rows <= 0) return 0;
   GENRL_REQUIRE(K <= 32 * KPL, "kl: K=%d unsupported", K);
@@ -1063,9 +1109,10 @@ extern "C" int genrl_actor_head_fwd(void* stream, const float* out, long long ld
 }
 
 extern "C" int genrl_actor_head_bwd(void* stream, const float* out, long long ldo, const float* eps, const void* daction, long long ldda,
-                                    const float* dent, float dent_scale, float* dout, long long lddo, long long rows, int A, int dtype) {
+                                    const float* dent, float dent_scale, void* dout, long long lddo, int dout_dtype, long long rows, int A, int dtype) {
   if (rows <= 0) return 0;
-  DISPATCH_T(dtype, (genrl::launch_pdl(actor_head_bwd_kernel<T>, ceil_div(rows, 128), 128, 0, ST(stream), out, ldo, eps, (const T*)daction, ldda, dent, dent_scale, dout, lddo, rows, A)));
+  GENRL_REQUIRE(dout_dtype == GENRL_F32 || dout_dtype == GENRL_BF16, "actor_head_bwd: bad output dtype %d", dout_dtype);
+  DISPATCH_T(dtype, (genrl::launch_pdl(actor_head_bwd_kernel<T>, ceil_div(rows, 128), 128, 0, ST(stream), out, ldo, eps, (const T*)daction, ldda, dent, dent_scale, dout, lddo, dout_dtype, rows, A)));
   return check_launch("actor_head_bwd");
 }
 

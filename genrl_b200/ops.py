@@ -735,7 +735,7 @@ class _ActorHead(Function):
         if eps is None:
             eps = torch.zeros(rows, A, device=out.device, dtype=torch.float32)
         lib.genrl_actor_head_bwd(_st(), _p(out), _ld(out), _p(eps), _p(daction), A, _p(dent), 1.0 if dent is not None else 0.0, _p(dout), 2 * A,
-                                 rows, A, F32)
+                                 F32, rows, A, F32)
         return dout, None, None, None
 
 

@@ -71,6 +71,11 @@ def _ln_bwd(dy, pre, gamma, beta, stats, dpre):
                          None, pre.shape[0], pre.shape[1], _CODE[pre.dtype])
 
 
+def _vec_ok(t):
+    """16-byte vector access: aligned base, leading dimension a multiple of 16 bytes"""
+    return t.data_ptr() % 16 == 0 and (_ld(t) * t.element_size()) % 16 == 0
+
+
 def _copy(src, dst, accumulate=False):
     lib.genrl_gather_rows(_st(), _p(src), _ld(src), _CODE[src.dtype], None, None, _p(dst), _ld(dst), _CODE[dst.dtype], dst.shape[0], src.shape[1],
                           int(accumulate))
@@ -206,7 +211,6 @@ class _Rollout(Function):
             a_dy = [_Slab(H, N, U, cd, dev) for _ in range(L)]
             a_dpre = [_Slab(H, N, U, cd, dev) for _ in range(L)]
             dout2c = _Slab(H, N, 2 * A, cd, dev, zero=True)
-            dout2 = torch.empty(N, 2 * A, device=dev, dtype=torch.float32)
             G = [torch.zeros(N, D, device=dev, dtype=torch.float32), torch.empty(N, D, device=dev, dtype=torch.float32)]     # d loss / d deter_i
             dlogit = torch.empty(N, SK, device=dev, dtype=torch.float32)
             dlogit_c = dlogit if cd == torch.float32 else _Slab(1, N, SK, cd, dev)[0]
@@ -232,10 +236,16 @@ class _Rollout(Function):
                 if dfeat is not None:
                     _copy(dfeat[i][:, SK:], gh, accumulate=True)
                 if srcs:
-                    for n_, s_ in enumerate(srcs):          # the straight-through backward is linear in d stoch: accumulate the contributions
-                        lib.genrl_cat_sample_bwd(_st(), _p(b["logit"][i]), _p(s_), _ld(s_), 1, _p(dlogit), int(n_ > 0), N, S, K, _CODE[s_.dtype])
-                    if dlogit_c is not dlogit:
-                        _copy(dlogit, dlogit_c)
+                    if K == 32 and len(srcs) <= 2 and all(s_.dtype == cd and _vec_ok(s_) for s_ in srcs) and _vec_ok(dlogit_c):
+                        # both contributions summed on the fly, gradient written in the activation dtype: one launch
+                        s2 = srcs[1] if len(srcs) == 2 else None
+                        lib.genrl_cat_sample_bwd2(_st(), _p(b["logit"][i]), _p(srcs[0]), _ld(srcs[0]), _p(s2), _ld(s2) if s2 is not None else 0,
+                                                  _p(dlogit_c), _ld(dlogit_c), N, S, K, _CODE[cd])
+                    else:
+                        for n_, s_ in enumerate(srcs):          # the straight-through backward is linear in d stoch: accumulate the contributions
+                            lib.genrl_cat_sample_bwd(_st(), _p(b["logit"][i]), _p(s_), _ld(s_), 1, _p(dlogit), int(n_ > 0), N, S, K, _CODE[s_.dtype])
+                        if dlogit_c is not dlogit:
+                            _copy(dlogit, dlogit_c)
                     ops.gemm(dlogit_c, W(lin_dist.weight), out=dy_out, trans_w=True)
                     _ln_bwd(dy_out, b["out_pre"][j], ln_out.weight, ln_out.bias, b["out_st"][j], dpre_out)
                     ops.gemm(dpre_out, W(lin_out.weight), out=gh, trans_w=True, accumulate=True)
@@ -254,8 +264,7 @@ class _Rollout(Function):
                     e = torch.zeros(N, A, device=dev, dtype=torch.float32)
                 de = None if dent is None else dent[j]
                 lib.genrl_actor_head_bwd(_st(), _p(b["out2"][j]), 2 * A, _p(e), _p(dxin[cur][:, SK:]), _ld(dxin[cur]), _p(de),
-                                         1.0 if de is not None else 0.0, _p(dout2), 2 * A, N, A, _CODE[cd])
-                _copy(dout2, dout2c[j])
+                                         1.0 if de is not None else 0.0, _p(dout2c[j]), _ld(dout2c[j]), _CODE[cd], N, A, _CODE[cd])
                 ops.gemm(dout2c[j], w_head, out=a_dy[L - 1][j], trans_w=True)
                 for l in range(L - 1, -1, -1):
                     _ln_bwd(a_dy[l][j], b["a_pre"][l][j], norms[l].weight, norms[l].bias, b["a_st"][l][j], a_dpre[l][j])

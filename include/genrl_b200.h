@@ -68,6 +68,9 @@ int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, u
                          int dtype);
 int genrl_cat_sample_bwd(void* stream, const float* logit, const void* dstoch, long long ld_ds, int sample, float* dlogit, int accumulate,
                          long long rows, int S, int K, int dtype);
+/* rollout backward (K = 32): straight-through backward of ds1 + ds2 (ds2 may be NULL), dlogit written in `dtype` with leading dimension ld_dl */
+int genrl_cat_sample_bwd2(void* stream, const float* logit, const void* ds1, long long ld1, const void* ds2, long long ld2, void* dlogit,
+                          long long ld_dl, long long rows, int S, int K, int dtype);
 
 /* Philox4x32-10 standard-normal fill (Normal.rsample noise, dreamer_utils.py:814-819; LAFITE noise, video_utils.py:143-146) and
  * the device-side step counter that keys every in-kernel generator (so CUDA-graph replays draw fresh noise). */
@@ -89,7 +92,7 @@ int genrl_twohot_bwd(void* stream, const float* logits, long long ldl, const flo
 int genrl_actor_head_fwd(void* stream, const float* out, long long ldo, const float* eps, int use_mean, float* action, long long lda,
                          void* action_t, long long ldat, float* ent, long long rows, int A, int dtype);
 int genrl_actor_head_bwd(void* stream, const float* out, long long ldo, const float* eps, const void* daction, long long ldda,
-                         const float* dent, float dent_scale, float* dout, long long lddo, long long rows, int A, int dtype);
+                         const float* dent, float dent_scale, void* dout, long long lddo, int dout_dtype, long long rows, int A, int dtype);
 
 /* lambda_return reverse scan: dreamer_utils.py:228-253. */
 int genrl_lambda_return_fwd(void* stream, const float* reward, const float* value, float gamma, float lambda, float* target, int H,

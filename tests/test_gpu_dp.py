@@ -55,6 +55,15 @@ class RecordedNoise:
 
 
 def _worker(rank, world, port, overlap, out):
+    try:
+        _worker_body(rank, world, port, overlap, out)
+    except Exception:
+        import traceback
+        out.put((rank, {"bad": [("exception", traceback.format_exc())], "n_allreduce": -1}))
+        raise
+
+
+def _worker_body(rank, world, port, overlap, out):
     import torch.distributed as dist
     from genrl_b200 import ops
     from genrl_b200.agent.genrl import GenRLAgent
@@ -108,7 +117,7 @@ def _worker(rank, world, port, overlap, out):
             a, b = hist_w[i][k], hist_p[i][k]
             if abs(a - b) > 2e-4 * max(1.0, abs(a)):
                 res["bad"].append((i, k, a, b))
-        t = torch.tensor([hist_p[i][k] for k in keys_mean], dtype=torch.float64)
+        t = torch.tensor([hist_p[i][k] for k in keys_mean], dtype=torch.float64, device=dev if backend == "nccl" else "cpu")
         dist.all_reduce(t)
         for k, v in zip(keys_mean, (t / world).tolist()):
             if abs(v - hist_w[i][k]) > 1e-4 * max(1.0, abs(hist_w[i][k])):
@@ -141,9 +150,15 @@ def test_two_ranks_on_half_batches_equal_one_rank_on_the_whole_batch(overlap):
         p.start()
     results = {}
     try:
-        for _ in range(world):
-            rank, res = q.get(timeout=600)
-            results[rank] = res
+        import queue, time
+        deadline = time.time() + 300
+        while len(results) < world and time.time() < deadline:
+            try:
+                rank, res = q.get(timeout=2)
+                results[rank] = res
+            except queue.Empty:
+                if any(p.exitcode not in (None, 0) for p in procs):      # a worker died: do not wait for its result
+                    break
     finally:
         for p in procs:
             p.join(timeout=60)
