@@ -76,6 +76,16 @@ def _vec_ok(t):
     return t.data_ptr() % 16 == 0 and (_ld(t) * t.element_size()) % 16 == 0
 
 
+_WGRAD_STREAMS = {}
+
+
+def _wgrad_stream(dev):
+    k = str(dev)
+    if k not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[k] = torch.cuda.Stream(device=dev)
+    return _WGRAD_STREAMS[k]
+
+
 def _copy(src, dst, accumulate=False):
     lib.genrl_gather_rows(_st(), _p(src), _ld(src), _CODE[src.dtype], None, None, _p(dst), _ld(dst), _CODE[dst.dtype], dst.shape[0], src.shape[1],
                           int(accumulate))
@@ -220,6 +230,38 @@ class _Rollout(Function):
             dx = _Slab(1, N, Hd, cd, dev)[0]
             dpre_in = _Slab(1, N, Hd, cd, dev)[0]
             dxin = [_Slab(1, N, SK + A, cd, dev)[0], _Slab(1, N, SK + A, cd, dev)[0]]
+            train = H > 0 and dense[0].weight.requires_grad
+
+            def param_grads(lo, hi):
+                """actor parameter gradients over the rollout steps lo..hi-1: one wgrad GEMM and one column pass per layer (the slabs are
+                contiguous, so the rows of several steps are one matrix)"""
+                st = _st()
+                for l in range(L):
+                    X = b["feat"].all(lo, hi) if l == 0 else b["a_y"][l - 1].all(lo, hi)
+                    DP, DY, PRE = a_dpre[l].all(lo, hi), a_dy[l].all(lo, hi), b["a_pre"][l].all(lo, hi)
+                    gbuf, _ = ops._grad_buf(dense[l].weight)
+                    ops.gemm(DP, X, out=gbuf.view(U, -1), trans_a=True, trans_w=True, accumulate=True)
+                    gb, _ = ops._grad_buf(norms[l].weight)
+                    bb, _ = ops._grad_buf(norms[l].bias)
+                    lb = ops._grad_buf(dense[l].bias)[0] if dense[l].bias is not None else None
+                    lib.genrl_ln_colgrad(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(DP), _ld(DP), _p(norms[l].weight), _p(norms[l].bias),
+                                         _p(b["a_st"][l][lo:hi].reshape(-1, 2)), ACT_SILU, _p(gb), _p(bb), _p(lb), DP.shape[0], U, _CODE[cd])
+                XH = b["a_y"][L - 1].all(lo, hi)
+                DO = dout2c.all(lo, hi)
+                for part, lin in ((0, policy._out._out), (1, policy._out._std)):
+                    gbuf, _ = ops._grad_buf(lin.weight)
+                    dsl = DO[:, part * A:(part + 1) * A]
+                    ops.gemm(dsl, XH, out=gbuf.view(A, U), trans_a=True, trans_w=True, accumulate=True)
+                    bbuf, _ = ops._grad_buf(lin.bias)
+                    lib.genrl_colsum(st, _p(dsl), _ld(dsl), _p(bbuf), dsl.shape[0], A, _CODE[cd])
+
+            # The step kernels of the backward loop run at 2 400 rows and leave most SMs idle, the parameter-gradient GEMMs run over
+            # thousands of rows: the gradients of the LATE half of the steps are computed on a side stream while the loop walks the early
+            # half (the two halves accumulate into the same flat buffers, so the early half waits for the late one).
+            mid = H // 2
+            forked = bool(train and H >= 4 and getattr(policy, "_overlap_wgrad", True) and dev.type == "cuda")
+            main_s = torch.cuda.current_stream()
+            side_s = _wgrad_stream(dev) if forked else None
             have_carry = False
             cur = 0
             for i in range(H, 0, -1):
@@ -272,27 +314,13 @@ class _Rollout(Function):
                         ops.gemm(a_dpre[l][j], W(dense[l].weight), out=a_dy[l - 1][j], trans_w=True)
                 have_carry = True
                 cur = 1 - cur
-            # ---- actor parameter gradients: one GEMM / one column pass per layer over all H*N rows --------------------------------------------
-            if H > 0 and dense[0].weight.requires_grad:
-                st = _st()
-                for l in range(L):
-                    X = b["feat"].all(0, H) if l == 0 else b["a_y"][l - 1].all()
-                    DP, DY, PRE = a_dpre[l].all(), a_dy[l].all(), b["a_pre"][l].all()
-                    gbuf, _ = ops._grad_buf(dense[l].weight)
-                    ops.gemm(DP, X, out=gbuf.view(U, -1), trans_a=True, trans_w=True, accumulate=True)
-                    gb, _ = ops._grad_buf(norms[l].weight)
-                    bb, _ = ops._grad_buf(norms[l].bias)
-                    lb = ops._grad_buf(dense[l].bias)[0] if dense[l].bias is not None else None
-                    lib.genrl_ln_colgrad(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(DP), _ld(DP), _p(norms[l].weight), _p(norms[l].bias),
-                                         _p(b["a_st"][l].reshape(-1, 2)), ACT_SILU, _p(gb), _p(bb), _p(lb), DP.shape[0], U, _CODE[cd])
-                XH = b["a_y"][L - 1].all()
-                DO = dout2c.all()
-                for part, lin in ((0, policy._out._out), (1, policy._out._std)):
-                    gbuf, _ = ops._grad_buf(lin.weight)
-                    dsl = DO[:, part * A:(part + 1) * A]
-                    ops.gemm(dsl, XH, out=gbuf.view(A, U), trans_a=True, trans_w=True, accumulate=True)
-                    bbuf, _ = ops._grad_buf(lin.bias)
-                    lib.genrl_colsum(st, _p(dsl), _ld(dsl), _p(bbuf), dsl.shape[0], A, _CODE[cd])
+                if forked and j == mid:
+                    side_s.wait_stream(main_s)
+                    with torch.cuda.stream(side_s):
+                        param_grads(mid, H)
+            main_s.wait_stream(side_s) if forked else None
+            if train and H > 0:
+                param_grads(0, mid if forked else H)
         return (None,) * (7 + ctx.n_params)
 
 
