@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="single-stream execution (no connector/critic overlap)")
     ap.add_argument("--eager", action="store_true", help="do not capture the update calls into CUDA graphs")
+    ap.add_argument("--preset", default="c2", choices=["c2", "c4", "c5"],
+                    help="BASELINE.json configs: c2 stickman (default) | c4 kitchen (A = 9, extra low-dimensional `state` observation key) | "
+                         "c5 large RSSM per-GPU shard (deter = hidden = 4096, stoch 48x48, batch 16x64, imag_horizon 32)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total sequences, split evenly over the ranks (default: --batch per rank, weak scaling)")
     ap.add_argument("--rollout-streams", type=int, default=1, help="row chunks of the imagination rollout enqueued on separate CUDA streams (measured: 2-4 chunks are 9-11 % slower, profiles/r02_notes.md)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
@@ -101,17 +104,35 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def apply_preset(args):
+    if args.preset == "c4":
+        args.action_dim = 9
+    elif args.preset == "c5":
+        args.batch, args.length, args.horizon = 16, 64, 32
+
+
 def make_cfg(args, device, precision):
-    from genrl_b200.config import genrl_config, make_specs
+    from genrl_b200.config import genrl_config, make_specs, Spec
     over = {"imag_reward_fn": "video_text_reward"} if getattr(args, "sequence", "S2") == "S3" else {}
+    if args.preset == "c5":
+        big = dict(ensemble=1, hidden=4096, deter=4096, stoch=48, discrete=48, norm="layer", std_act="softplus", min_std=0.1)
+        over.update(rssm=dict(big, single_obs_posterior=True), connector_rssm=dict(big, single_obs_posterior=False, learn_initial=True))
     cfg = genrl_config(device=device, precision=precision, batch_size=args.batch, batch_length=args.length, imag_horizon=args.horizon, **over)
     obs_space, act_spec = make_specs(action_dim=args.action_dim, clip_dim=512)
+    if args.preset == "c4":
+        obs_space["state"] = Spec((30,), "float32")
     return cfg, obs_space, act_spec
+
+
+EXTRA_KEYS = {}
 
 
 def synthetic(B, T, A, seed):
     from genrl_b200.synthetic import synthetic_batch
-    return synthetic_batch(B, T, A, clip_dim=512, seed=seed)
+    d = synthetic_batch(B, T, A, clip_dim=512, seed=seed)
+    for k, n in EXTRA_KEYS.items():
+        d[k] = torch.zeros(B, T, n)
+    return d
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -176,8 +197,10 @@ SEQ_TEXT = {"S1": "S1 (update_wm incl. connector)", "S2": "S2 (update_wm incl. c
 
 
 def workload_config(args):
-    return {"workload": f"GenRL full update {SEQ_TEXT[args.sequence]}, stickman A={args.action_dim}, "
-                        f"per-GPU batch {args.batch}x{args.length}, 64x64x3 u8 obs, deter=1024, stoch=32x32, imag_horizon={args.horizon}",
+    env = {"c2": "stickman", "c4": "kitchen (extra `state` key)", "c5": "stickman, large RSSM"}[args.preset]
+    dims = "deter=4096, stoch=48x48" if args.preset == "c5" else "deter=1024, stoch=32x32"
+    return {"workload": f"GenRL full update {SEQ_TEXT[args.sequence]}, {env} A={args.action_dim}, "
+                        f"per-GPU batch {args.batch}x{args.length}, 64x64x3 u8 obs, {dims}, imag_horizon={args.horizon}", "preset": args.preset,
             "batch": args.batch, "length": args.length, "horizon": args.horizon, "parallelism": f"dp{args.gpus}",
             "l2": "5 rotating input batches (150 MB) and a multi-GB per-step working set exceed the 126 MB L2"}
 
@@ -538,6 +561,9 @@ def cpu_baseline(args, agent):
 
 if __name__ == "__main__":
     a = parse()
+    apply_preset(a)
+    if a.preset == "c4":
+        EXTRA_KEYS["state"] = 30
     if a.impl == "reference":
         run_reference(a)
     else:

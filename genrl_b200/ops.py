@@ -170,6 +170,24 @@ def gemm(a, w, out=None, bias=None, trans_a=False, trans_w=False, accumulate=Fal
     return out
 
 
+def gemm_pair(a, w, out=None, bias=None, trans_w=False, out_dtype=None):
+    """out[M,N] = a @ op(w)^T + bias on the persistent 2-CTA kernel (csrc/gemm_pair.cu); bf16 operands.  Returns None if the shape is not eligible."""
+    _check(a, "gemm A"); _check(w, "gemm W")
+    M, K = a.shape
+    N, K2 = (w.shape[1], w.shape[0]) if trans_w else (w.shape[0], w.shape[1])
+    if K != K2 or a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        raise GenrlError("gemm_pair: bf16 operands with matching inner dimension required")
+    if out is None:
+        out = empty_act(M, N, a.device, out_dtype or a.dtype)
+    rc = lib.load().genrl_gemm_pair(_st(), M, N, K, _p(a), _ld(a), _p(w), _ld(w), int(trans_w), _p(out), _ld(out), _CODE[out.dtype], _p(bias))
+    if rc == 2:
+        return None
+    if rc != 0:
+        raise GenrlError(f"genrl_gemm_pair failed: {lib.load().genrl_last_error().decode()}")
+    lib.launches += 1
+    return out
+
+
 def as_compute(t):
     t = _check(t)
     return t if t.dtype == _State.dtype else cast_to(t, _State.dtype)

@@ -28,6 +28,11 @@ int genrl_debug_occupancy();   /* prints kernel attributes / occupancy to stderr
 int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W, long long ldw, int transW,
                int in_dtype, void* C, long long ldc, int c_dtype, const float* bias, int accumulate);
 
+/* The same GEMM on the persistent 2-CTA kernel (tcgen05.mma.cta_group::2, 256x256 tile per CTA pair, csrc/gemm_pair.cu): bf16 operands,
+ * A [M,K] K-major, W [N,K] (transW = 0) or [K,N] (transW = 1), no accumulate.  Returns 2 if the shape is not eligible. */
+int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, int transW, void* C,
+                    long long ldc, int c_dtype, const float* bias);
+
 /* Linear + LayerNorm(+SiLU) fused (bf16, N multiple of 128 up to 1024): the N/128 column-tile CTAs of a row stripe form a thread-block
  * cluster and merge their per-row (mean, M2) partials through distributed shared memory.  Replaces Linear -> NormLayer -> act
  * (dreamer_utils.py:738-744, :339-346).  pre is kept for the backward pass; stats[M][2] = (mean, rstd). */

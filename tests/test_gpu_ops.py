@@ -576,3 +576,23 @@ def test_mlp_chain_fwd_matches_layerwise_reference(M, K0, N, L):
         ref_y = F.silu(F.layer_norm(ref_pre, (N,), gs[l], bt[l], 1e-5))
         close(y[l], ref_y, rtol=1e-2, atol=2e-2, msg=f"layer {l} y")
         inp = y[l]
+
+
+@pytest.mark.parametrize("tw,M,N,K", [(False, 2400, 1024, 1024), (False, 5000, 1024, 2048), (True, 2400, 1024, 1024), (False, 300, 256, 1040),
+                                      (True, 38400, 2048, 1024), (False, 1000, 3072, 2048), (False, 257, 384, 64)])
+def test_gemm_pair_2cta(tw, M, N, K):
+    """2-CTA tcgen05 GEMM (csrc/gemm_pair.cu) vs an fp32 matmul of the same bf16 operands, K-major and MN-major weights, bias, ragged tiles"""
+    g = torch.Generator().manual_seed(M + N + K)
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 8))[:, :t.shape[1]]
+    a = pad(torch.randn(M, K, generator=g).to(DEV, torch.bfloat16))
+    w = pad((torch.randn(K, N, generator=g) if tw else torch.randn(N, K, generator=g)).to(DEV, torch.bfloat16))
+    bias = torch.randn(N, generator=g).to(DEV)
+    for out_dtype in (torch.bfloat16, torch.float32):
+        out = ops.gemm_pair(a, w, bias=bias, trans_w=tw, out_dtype=out_dtype)
+        assert out is not None
+        ref = a.float() @ (w.float() if tw else w.float().t()) + bias
+        close(out, ref, rtol=1e-2 if out_dtype == torch.bfloat16 else 2e-3, atol=1e-1 if out_dtype == torch.bfloat16 else 2e-2, msg=f"pair gemm {out_dtype}")
+    # several launches back to back (persistent pipeline state / barrier phases start clean every launch)
+    for _ in range(3):
+        out2 = ops.gemm_pair(a, w, bias=bias, trans_w=tw, out_dtype=torch.float32)
+    close(out2, ref, rtol=2e-3, atol=2e-2, msg="pair gemm repeat")
