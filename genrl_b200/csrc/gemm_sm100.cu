@@ -730,6 +730,9 @@ using namespace genrl;
 // C[M,N] (+)= op(A) * op(W)^T + bias.  A: [M,K] row-major (lda) or, if transA, [K,M] row-major (lda).
 // W: [N,K] row-major (ldw) or, if transW, [K,N] row-major (ldw).  in_dtype: GENRL_F32 (SIMT) or
 // GENRL_BF16 (tcgen05).  C: [M,N] row-major (ldc) of c_dtype; accumulate requires fp32 C.
+extern "C" int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, int transW, void* C,
+                               long long ldc, int c_dtype, const float* bias);
+
 extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W,
                           long long ldw, int transW, int in_dtype, void* C, long long ldc, int c_dtype, const float* bias,
                           int accumulate) {
@@ -757,6 +760,18 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
   // GENRL_GEMM_PERSIST: 0 = never, 2 = whenever the kernel supports the call (tests), default = large-M shapes only
   const char* pm = getenv("GENRL_GEMM_PERSIST");
   const int persist_mode = pm ? atoi(pm) : 1;
+  // 2-CTA kernel (gemm_pair.cu) first: measured 1.18-1.27 PFLOP/s on the 38 400-row shapes against 0.98 for the 256x128 single-CTA
+  // persistent kernel (cuBLASLt: 1.21-1.23), and ahead of the 128x128 kernel from ~64 pair tiles up (2400x3072x2048: 28.7 vs 34.6 us);
+  // below that a launch has fewer 256x256 tiles than CTA pairs and the 128x128 kernel's two CTAs per SM win (tools/gemm_bar.py)
+  static int pair_mode = -1;
+  if (pair_mode < 0) { const char* e = getenv("GENRL_GEMM_PAIR"); pair_mode = e ? atoi(e) : 1; }
+  if (pair_mode && !transA && !accumulate && N % 128 == 0) {
+    const long long pair_tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
+    if (pair_mode == 2 || pair_tiles >= 64) {
+      const int rc = genrl_gemm_pair(stream, M, N, K, A, lda, W, ldw, transW, C, ldc, c_dtype, bias);
+      if (rc != 2) return rc;
+    }
+  }
   const bool persist_ok = !transA && !accumulate;
   // measured (tools/debug_pgemm.py): 1.02-1.15 PFLOP/s vs 0.79-1.0 for N >= 1024; N = 255 (300 tiles = 2.03 waves) loses to the 128x128 kernel
   const bool persist_auto = M >= 8192 && N >= 512 && (long long)ceil_div(M, PG_BM) * ceil_div(N, PG_BN) >= 4 * num_sms();
