@@ -448,6 +448,10 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
         counts["gemm_flops"] += 2.0 * a[1] * a[2] * a[3]; counts["gemm_calls"] += 1
     hook("genrl_gemm", on_gemm)
     hook("genrl_gemm_ln_fwd", on_gemm)
+
+    def on_chain(a):          # (stream, M, N, L, x, ldx, K0, ...): layer 0 has K0 inputs, the others N
+        counts["gemm_flops"] += 2.0 * a[1] * a[2] * (a[6] + (a[3] - 1) * a[2]); counts["gemm_calls"] += 1
+    hook("genrl_mlp_chain_fwd", on_chain)
     hook("genrl_rssm_scan_fwd", lambda a: counts.__setitem__("scan_calls", counts["scan_calls"] + 1))
     step(devb[0], 0)
     torch.cuda.synchronize()
@@ -465,7 +469,7 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
     breakdown["_total"] = {"kernel_ms_per_step": total_us / n / 1e3, "launches_per_step": sum(v[0] for v in agg.values()) / n,
                            "step_ms": ms_step, "source": f"CUPTI (torch.profiler) over {n} graph-replayed steps"}
     fam = lambda *pats: [sum(v[0] for k, v in agg.items() if any(p in k for p in pats)), sum(v[1] for k, v in agg.items() if any(p in k for p in pats))]
-    g_l, g_us = fam("gemm_tc_kernel", "gemm_tc_persist_kernel", "gemm_ln_kernel", "gemm_simt_kernel")
+    g_l, g_us = fam("gemm_tc_kernel", "gemm_tc_persist_kernel", "gemm_ln_kernel", "gemm_simt_kernel", "gemm_pair_kernel", "mlp_chain_fwd_kernel")
     roof = None
     if g_us > 0:
         achieved = counts["gemm_flops"] * n / (g_us * 1e-6) / 1e12
@@ -474,7 +478,8 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
         tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if bf16 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")      # ncu dram__bytes_read+write, mean over the step's GEMM launches
-        roof = {"kernel": "gemm_tc_kernel + gemm_tc_persist_kernel + gemm_ln_kernel (tcgen05)" if bf16 else "gemm_simt_kernel (fp32 parity mode)",
+        roof = {"kernel": "tcgen05 GEMM family: gemm_tc_kernel (128xBN), gemm_pair_kernel (2-CTA 256x256), mlp_chain_fwd_kernel (Linear+LN chains), "
+                          "gemm_tc_persist_kernel, gemm_ln_kernel" if bf16 else "gemm_simt_kernel (fp32 parity mode)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": (pk["source"] + " bf16 sustained") if bf16 else "nominal fp32 FFMA",
                 "share_of_step": g_us / total_us, "launch_avg_us": g_us / g_l, "launches_per_step": g_l / n,
