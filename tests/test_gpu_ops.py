@@ -106,6 +106,31 @@ def test_ln_act(dtype, M, D, eps, act):
         close(bd.grad, br.grad, msg="ln dbeta", **(tol if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)))
 
 
+@pytest.mark.parametrize("M,D,eps,act,train", [(9000, 1024, 1e-5, 1, True), (20011, 48, 1e-3, 1, True), (8200, 384, 1e-3, 1, True),
+                                                (8197, 96, 1e-3, 1, True), (16000, 192, 1e-3, 1, False), (12288, 1024, 1e-5, 1, False),
+                                                (8192, 512, 1e-5, 0, True), (8300, 256, 1e-5, 1, True)])
+def test_ln_bwd_tile_staged_large_rows(M, D, eps, act, train):
+    """>= 8192 bf16 rows take the shared-memory-staged LayerNorm backward (csrc/ln_tile.cuh): dx and the fused dgamma / dbeta vs torch fp32 on
+    the same bf16 inputs; with frozen parameters (train = False) the same kernel runs without the column partials"""
+    with ops.use_dtype(torch.bfloat16):
+        x = rnd(M, D).to(torch.bfloat16)
+        g, b = 1 + 0.1 * rnd(D, seed=1), 0.1 * rnd(D, seed=2)
+        dy = rnd(M, D, seed=3).to(torch.bfloat16)
+        xr = x.float().clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        y = F.layer_norm(xr, (D,), gr, br, eps)
+        y = F.silu(y) if act else y
+        y.backward(dy.float())
+        xd = x.to(DEV).requires_grad_(True)
+        gd = torch.nn.Parameter(g.to(DEV), requires_grad=train); bd = torch.nn.Parameter(b.to(DEV), requires_grad=train)
+        yd = ops.ln_act(xd, gd, bd, eps, act)
+        yd.backward(dy.to(DEV))
+        close(xd.grad, xr.grad, msg="ln dx", rtol=2e-2, atol=2e-2)
+        if train:
+            # column sums over ~10^4 rows of bf16-rounded dx: compare against the scale of the sums
+            close(gd.grad, gr.grad, msg="ln dgamma", rtol=2e-2, atol=5e-2)
+            close(bd.grad, br.grad, msg="ln dbeta", rtol=2e-2, atol=5e-2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,K,N", [(130, 72, 64), (200, 264, 128), (333, 1034, 512), (2400, 2048, 1024)])
 def test_linear_ln_act_and_linear(dtype, M, K, N, monkeypatch):
