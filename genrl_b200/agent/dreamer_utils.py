@@ -69,37 +69,6 @@ class MSEDist:
         return like.reshape(lead)
 
 
-class FusedImageDist:
-    """MSEDist over the decoder's last ConvTranspose2d, evaluated lazily: log_prob(uint8 obs) runs the fused
-    convT + likelihood kernel (no im2col/col2im buffers); .mean materialises the image only when asked for."""
-
-    def __init__(self, x_rows, conv, N, Hi, Wi, lead):
-        self._x, self._conv, self._geom, self._lead = x_rows, conv, (N, Hi, Wi), lead
-        self._mean = None
-
-    def _materialise(self):
-        if self._mean is None:
-            N, Hi, Wi = self._geom
-            y, _, _ = ops.conv_transpose2d_s2(self._x, self._conv.weight, self._conv.bias, N, Hi, Wi, 6, nchw_out=True)
-            self._mean = y.reshape(self._lead + tuple(y.shape[1:]))
-        return self._mean
-
-    @property
-    def mean(self):
-        return self._materialise()
-
-    def mode(self):
-        return self._materialise()
-
-    def log_prob(self, value):
-        N, Hi, Wi = self._geom
-        if value.dtype != torch.uint8:
-            return MSEDist(self._materialise()).log_prob(value)
-        like, mean = ops.convT3_mse(self._x, self._conv.weight, self._conv.bias, value.reshape((N,) + tuple(value.shape[-3:])), N, Hi, Wi)
-        self._mean = mean.reshape(self._lead + tuple(mean.shape[1:]))
-        return like.reshape(self._lead)
-
-
 class TwoHotDist:
     """reference dreamer_utils.py:120-171; logits fp32 [..., 255]"""
 
@@ -571,11 +540,6 @@ class Encoder(Module):
         h, w = H, W
         for i, k in enumerate(self._cnn_kernels):
             conv, ln = self._conv_model[3 * i], self._conv_model[3 * i + 1].norm
-            if i == 0 and k == 4 and C == 3 and code == ACT_SILU and w % 2 == 0 and ops.thin_conv_supported(conv.weight.shape[0]):
-                # 3-channel first layer: direct fused kernel (conv + bias + channel-LN + SiLU, preprocessing included)
-                x = ops.conv0_ln_silu(x, conv.weight, conv.bias, ln.weight, ln.bias, ln.eps)
-                h, w = (h - k) // 2 + 1, (w - k) // 2 + 1
-                continue
             x, h, w = ops.conv2d_s2(x, conv.weight, conv.bias, N, h, w, k, u8=(i == 0))
             x = ops.ln_act(x, ln.weight, ln.bias, ln.eps, code)
         Cl = x.shape[1]
@@ -625,9 +589,6 @@ class Decoder(Module):
         for i, k in enumerate(self._cnn_kernels):
             conv = self._conv_model[3 * i]
             last = i == n_l - 1
-            if last and k == 6 and conv.weight.shape[1] == 3 and ops.thin_conv_supported(conv.weight.shape[0]) and \
-                    (((h - 1) * 2 + k) * ((w - 1) * 2 + k)) % 32 == 0:
-                return {self.cnn_keys[0]: FusedImageDist(x, conv, N, h, w, lead)}
             x, h, w = ops.conv_transpose2d_s2(x, conv.weight, conv.bias, N, h, w, k, nchw_out=last)
             if not last:
                 ln = self._conv_model[3 * i + 1].norm

@@ -4,7 +4,6 @@
 // Each forward has a hand-written backward (no autograd inside the library).
 #include "common.cuh"
 #include "rowops_fast.cuh"
-#include "ln_tile.cuh"
 #include <algorithm>
 
 namespace genrl {
@@ -885,7 +884,6 @@ static int num_sms_rows() {
   if (n == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
   return n;
 }
-constexpr long long LN_TILE_MIN_ROWS = 8192;
 static inline int ln_lpr(int D, int nch) { int l = 1; while (l * 8 * nch < D) l *= 2; return l; }
 
 extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
@@ -912,28 +910,6 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   if (M <= 0) return 0;
   GENRL_REQUIRE(3 * D * 4 <= 200 * 1024, "ln_act_bwd: D too large");
   size_t smem = (size_t)3 * D * sizeof(float);
-  // large row counts in bf16: tile-staged kernel (ln_tile.cuh)
-  static int tile_mode = -1;
-  if (tile_mode < 0) { const char* e = getenv("GENRL_LN_TILE"); tile_mode = e ? atoi(e) : 1; }
-  if (tile_mode && dtype == GENRL_BF16 && M >= LN_TILE_MIN_ROWS && vec_ok<__nv_bfloat16>(x, ldx) && vec_ok<__nv_bfloat16>(dy, lddy) &&
-      vec_ok<__nv_bfloat16>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
-    LnTileCfg cfg;
-    if (ln_tile_config(D, 2, &cfg)) {
-      static bool attr_set = false;
-      static int bps = 0;
-      if (!attr_set) {
-        cudaFuncSetAttribute(ln_bwd_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
-      }
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, ln_bwd_tile_kernel<__nv_bfloat16>, cfg.threads, cfg.smem);
-      if (bps <= 0) bps = 1;
-      const long long ntiles = (M + cfg.rows - 1) / cfg.rows;
-      const int grid = (int)std::min<long long>(ntiles, (long long)num_sms_rows() * bps);
-      genrl::launch_pdl(ln_bwd_tile_kernel<__nv_bfloat16>, grid, cfg.threads, cfg.smem, ST(stream), (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx,
-                        gamma, beta, stats, act, (__nv_bfloat16*)dx, lddx, dgamma, dbeta, dlin_bias, M, D, cfg.rows, cfg.lpr);
-      return check_launch("ln_bwd_tile");
-    }
-  }
   DISPATCH_T(dtype, {
     if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       if (dgamma || dlin_bias) {

@@ -1040,89 +1040,6 @@ def conv_transpose2d_s2(x, w, b, N, Hi, Wi, k, nchw_out=False):
     return _ConvT2dS2.apply(x, w, b, (N, Hi, Wi, k, Ho, Wo, nchw_out)), Ho, Wo
 
 
-def thin_conv_supported(channels):
-    """The direct fused thin-conv kernels (thin_conv.cu) are parity-tested but, in their current FFMA form, not yet faster than
-    the lowered path on B200 (profiles/r01_notes.md); they are opt-in via GENRL_THIN_CONV=1."""
-    import os
-    if os.environ.get("GENRL_THIN_CONV", "0") != "1":
-        return False
-    return bool(lib.load().genrl_thin_conv_supported(int(channels)))
-
-
-class _Conv0LnSilu(Function):
-    """Encoder layer 0 fused: uint8 NCHW -> Conv2d(3->C,k4,s2)+b -> LayerNorm(C) -> SiLU (thin_conv.cu); backward recomputes the conv."""
-
-    @staticmethod
-    def forward(ctx, obs, w, b, gamma, beta, eps):
-        N, _, H, W = obs.shape
-        C = w.shape[0]
-        Ho, Wo = (H - 4) // 2 + 1, (W - 4) // 2 + 1
-        dt = _State.dtype
-        y = torch.empty(N * Ho * Wo, C, device=obs.device, dtype=dt)
-        stats = torch.empty(N * Ho * Wo, 2, device=obs.device, dtype=torch.float32)
-        lib.genrl_conv0_ln_silu_fwd(_st(), _p(obs), _p(w.detach()), _p(b.detach()), _p(gamma.detach()), _p(beta.detach()), eps, _p(y), _p(stats),
-                                    N, H, W, C, _CODE[dt])
-        ctx.save_for_backward(obs, stats)
-        ctx.params, ctx.geom = (w, b, gamma, beta), (N, H, W, C)
-        return y
-
-    @staticmethod
-    def backward(ctx, dy):
-        obs, stats = ctx.saved_tensors
-        w, b, gamma, beta = ctx.params
-        N, H, W, C = ctx.geom
-        dy = dy.contiguous()
-        outs = [None] * 6
-        if ctx.needs_input_grad[1]:
-            (gw, rw), (gb, rb), (gg, rg), (gbt, rbt) = _grad_buf(w), _grad_buf(b), _grad_buf(gamma), _grad_buf(beta)
-            lib.genrl_conv0_ln_silu_bwd(_st(), _p(obs), _p(w.detach()), _p(b.detach()), _p(gamma.detach()), _p(beta.detach()), _p(stats), _p(dy),
-                                        _p(gw), _p(gb), _p(gg), _p(gbt), N, H, W, C, _CODE[dy.dtype])
-            outs[1:5] = [rw, rb, rg, rbt]
-        return tuple(outs)
-
-
-def conv0_ln_silu(obs_u8, w, b, gamma, beta, eps):
-    """returns NHWC rows [N*Ho*Wo, C] in the compute dtype"""
-    return _Conv0LnSilu.apply(obs_u8.contiguous(), w, b, gamma, beta, float(eps))
-
-
-class _ConvT3Mse(Function):
-    """Decoder last layer fused with the image likelihood: like[n] = -sum_chw (ConvT(x)+b - (obs/255-0.5))^2 (thin_conv.cu)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b, obs, geom):
-        N, Hi, Wi = geom
-        C = w.shape[0]
-        x = as_compute(x)
-        Ho, Wo = (Hi - 1) * 2 + 6, (Wi - 1) * 2 + 6
-        mean = torch.empty(N, 3, Ho, Wo, device=x.device, dtype=torch.float32)
-        like = torch.empty(N, device=x.device, dtype=torch.float32)
-        lib.genrl_convT3_mse_fwd(_st(), _p(x), _p(w.detach()), _p(b.detach()), _p(obs), _p(mean), _p(like), N, Hi, Wi, C, _CODE[x.dtype])
-        ctx.save_for_backward(x, mean, obs)
-        ctx.params, ctx.geom = (w, b), geom
-        ctx.mark_non_differentiable(mean)
-        return like, mean
-
-    @staticmethod
-    def backward(ctx, dlike, _dmean):
-        x, mean, obs = ctx.saved_tensors
-        w, b = ctx.params
-        N, Hi, Wi = ctx.geom
-        C = w.shape[0]
-        dlike = dlike.contiguous().float()
-        dx = torch.empty_like(x)
-        gw, rw = _grad_buf(w)
-        gb, rb = _grad_buf(b)
-        lib.genrl_convT3_mse_bwd(_st(), _p(x), _p(w.detach()), _p(mean), _p(obs), _p(dlike), _p(dx), _p(gw), _p(gb), N, Hi, Wi, C, _CODE[x.dtype])
-        train = ctx.needs_input_grad[1]
-        return dx, (rw if train else None), (rb if train else None), None, None
-
-
-def convT3_mse(x_rows, w, b, obs_u8, N, Hi, Wi):
-    """x_rows [N*Hi*Wi, C] -> (like [N], mean fp32 [N,3,Ho,Wo])"""
-    return _ConvT3Mse.apply(x_rows, w, b, obs_u8.contiguous(), (N, Hi, Wi))
-
-
 class _PermuteABP(Function):
     """[A, B, P] -> [A, P, B] rows (used for NHWC <-> (C,H,W) flatten order of the encoder output)."""
 

@@ -159,19 +159,6 @@ int genrl_nchw_to_nhwc_pad(void* stream, const float* x, void* y, long long N, i
 int genrl_u8_nchw_to_nhwc8(void* stream, const void* x, void* y, long long N, int C, int H, int W);
 int genrl_permute_abp(void* stream, const void* src, int src_dtype, void* dst, int dst_dtype, long long A, int B, int P, int accumulate);
 
-/* Fused direct kernels for the 3-channel ends of the conv stacks (Encoder layer 0 + ImgChLayerNorm + SiLU, dreamer_utils.py:580-589;
- * Decoder last ConvTranspose2d + MSEDist.log_prob, :656-671,:74-83).  Gradients of parameters are accumulated (+=). */
-int genrl_thin_conv_supported(int channels);
-int genrl_conv0_ln_silu_fwd(void* stream, const unsigned char* obs, const float* w, const float* bias, const float* gamma, const float* beta,
-                            float eps, void* y, float* stats, int N, int H, int W, int C, int dtype);
-int genrl_conv0_ln_silu_bwd(void* stream, const unsigned char* obs, const float* w, const float* bias, const float* gamma, const float* beta,
-                            const float* stats, const void* dy, float* dW, float* db, float* dgamma, float* dbeta, int N, int H, int W, int C,
-                            int dtype);
-int genrl_convT3_mse_fwd(void* stream, const void* x, const float* w, const float* bias, const unsigned char* obs, float* mean_out, float* like,
-                         int N, int Hi, int Wi, int C, int dtype);
-int genrl_convT3_mse_bwd(void* stream, const void* x, const float* w, const float* mean, const unsigned char* obs, const float* dlike, void* dx,
-                         float* dW, float* db, int N, int Hi, int Wi, int C, int dtype);
-
 /* Optimizer.__call__: dreamer_utils.py:892-932 (clip -> weight decay -> Adam) on flat fp32 buffers. */
 int genrl_grad_sumsq(void* stream, const float* g, long long n, float* sumsq_out, int zero_first);
 int genrl_scale(void* stream, float* p, long long n, float s);

@@ -106,31 +106,6 @@ def test_ln_act(dtype, M, D, eps, act):
         close(bd.grad, br.grad, msg="ln dbeta", **(tol if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)))
 
 
-@pytest.mark.parametrize("M,D,eps,act,train", [(9000, 1024, 1e-5, 1, True), (20011, 48, 1e-3, 1, True), (8200, 384, 1e-3, 1, True),
-                                                (8197, 96, 1e-3, 1, True), (16000, 192, 1e-3, 1, False), (12288, 1024, 1e-5, 1, False),
-                                                (8192, 512, 1e-5, 0, True), (8300, 256, 1e-5, 1, True)])
-def test_ln_bwd_tile_staged_large_rows(M, D, eps, act, train):
-    """>= 8192 bf16 rows take the shared-memory-staged LayerNorm backward (csrc/ln_tile.cuh): dx and the fused dgamma / dbeta vs torch fp32 on
-    the same bf16 inputs; with frozen parameters (train = False) the same kernel runs without the column partials"""
-    with ops.use_dtype(torch.bfloat16):
-        x = rnd(M, D).to(torch.bfloat16)
-        g, b = 1 + 0.1 * rnd(D, seed=1), 0.1 * rnd(D, seed=2)
-        dy = rnd(M, D, seed=3).to(torch.bfloat16)
-        xr = x.float().clone().requires_grad_(True); gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
-        y = F.layer_norm(xr, (D,), gr, br, eps)
-        y = F.silu(y) if act else y
-        y.backward(dy.float())
-        xd = x.to(DEV).requires_grad_(True)
-        gd = torch.nn.Parameter(g.to(DEV), requires_grad=train); bd = torch.nn.Parameter(b.to(DEV), requires_grad=train)
-        yd = ops.ln_act(xd, gd, bd, eps, act)
-        yd.backward(dy.to(DEV))
-        close(xd.grad, xr.grad, msg="ln dx", rtol=2e-2, atol=2e-2)
-        if train:
-            # column sums over ~10^4 rows of bf16-rounded dx: compare against the scale of the sums
-            close(gd.grad, gr.grad, msg="ln dgamma", rtol=2e-2, atol=5e-2)
-            close(bd.grad, br.grad, msg="ln dbeta", rtol=2e-2, atol=5e-2)
-
-
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,K,N", [(130, 72, 64), (200, 264, 128), (333, 1034, 512), (2400, 2048, 1024)])
 def test_linear_ln_act_and_linear(dtype, M, K, N, monkeypatch):
@@ -482,61 +457,6 @@ def test_gru_scan_matches_stepwise(dtype, B, T, D, Hd, resets):
         close(gd.grad, gr.grad, msg="scan dgamma", **tol)
         close(bd.grad, br.grad, msg="scan dbeta", **tol)
         close(wd.grad[:, Hd:], wr.grad[:, Hd:], msg="scan dW_h", **tol)
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_thin_conv0_fused(dtype):
-    """fused encoder layer 0 (conv + channel-LN + SiLU from uint8) vs torch, C = 48"""
-    N, H, C = 3, 64, 48
-    with ops.use_dtype(dtype):
-        torch.manual_seed(0)
-        conv = torch.nn.Conv2d(3, C, 4, stride=2); ln = torch.nn.LayerNorm(C, eps=1e-3)
-        with torch.no_grad():
-            ln.weight.add_(0.1 * torch.randn(C)); ln.bias.add_(0.1 * torch.randn(C))
-        x8 = torch.randint(0, 256, (N, 3, H, H), dtype=torch.uint8)
-        x = x8.float() / 255.0 - 0.5
-        wr = conv.weight.detach().clone().requires_grad_(True); br = conv.bias.detach().clone().requires_grad_(True)
-        gr = ln.weight.detach().clone().requires_grad_(True); ber = ln.bias.detach().clone().requires_grad_(True)
-        y = F.conv2d(x, wr, br, stride=2).permute(0, 2, 3, 1)
-        y = F.silu(F.layer_norm(y, (C,), gr, ber, 1e-3))
-        dy = rnd(*y.shape, seed=3).to(dtype).float()
-        y.backward(dy)
-        cd, ld = conv.to(DEV), ln.to(DEV)
-        yd = ops.conv0_ln_silu(x8.to(DEV), cd.weight, cd.bias, ld.weight, ld.bias, 1e-3)
-        yd.backward(dy.reshape(-1, C).to(DEV).to(dtype))
-        tol = dict(rtol=1e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
-        close(yd.reshape(y.shape), y, msg="conv0 fused y", **tol)
-        gtol = dict(rtol=2e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
-        close(cd.weight.grad, wr.grad, msg="conv0 fused dW", **gtol)
-        close(cd.bias.grad, br.grad, msg="conv0 fused db", **gtol)
-        close(ld.weight.grad, gr.grad, msg="conv0 fused dgamma", **gtol)
-        close(ld.bias.grad, ber.grad, msg="conv0 fused dbeta", **gtol)
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_thin_convT3_mse_fused(dtype):
-    """fused decoder last layer + image likelihood vs torch, C = 48"""
-    N, Hi, C = 3, 30, 48
-    with ops.use_dtype(dtype):
-        torch.manual_seed(0)
-        conv = torch.nn.ConvTranspose2d(C, 3, 6, stride=2)
-        x = (rnd(N, C, Hi, Hi) * 0.5).to(dtype).float()
-        obs = torch.randint(0, 256, (N, 3, 64, 64), dtype=torch.uint8)
-        xr = x.clone().requires_grad_(True); wr = conv.weight.detach().clone().requires_grad_(True); br = conv.bias.detach().clone().requires_grad_(True)
-        mean = F.conv_transpose2d(xr, wr, br, stride=2)
-        like = -((mean - (obs.float() / 255.0 - 0.5)) ** 2).sum(dim=(1, 2, 3))
-        g = rnd(N, seed=5)
-        like.backward(g)
-        cd = conv.to(DEV)
-        xd = x.permute(0, 2, 3, 1).reshape(N * Hi * Hi, C).to(DEV).to(dtype).requires_grad_(True)
-        ld, md = ops.convT3_mse(xd, cd.weight, cd.bias, obs.to(DEV), N, Hi, Hi)
-        ld.backward(g.to(DEV))
-        tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
-        close(md, mean, msg="convT3 mean", **tol)
-        close(ld, like, msg="convT3 like", **(dict(rtol=1e-4, atol=1e-2) if dtype == torch.float32 else dict(rtol=2e-2, atol=1.0)))
-        close(xd.grad.reshape(N, Hi, Hi, C).permute(0, 3, 1, 2), xr.grad, msg="convT3 dx", **tol)
-        close(cd.weight.grad, wr.grad, msg="convT3 dW", **tol)
-        close(cd.bias.grad, br.grad, msg="convT3 db", **tol)
 
 
 @pytest.mark.parametrize("dtype,T,N,E,align", [(torch.float32, 11, 37, 96, True), (torch.float32, 16, 64, 1536, True),
