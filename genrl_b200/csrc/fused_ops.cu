@@ -871,6 +871,23 @@ __global__ void __launch_bounds__(256) fill_normal_kernel(float* __restrict__ ou
     for (int k = 0; k < 4; ++k) if (i * 4 + k < n) out[i * 4 + k] = z[k];
   }
 }
+// fp32 -> three bf16 terms with x = hi + mid + lo to ~2^-24 relative (the operands of the "bf16x3" tensor-core GEMM of the fp32 parity mode)
+__global__ void __launch_bounds__(256) split3_bf16_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ mid, __nv_bfloat16* __restrict__ lo, long long ldd,
+                                                          long long rows, int cols) {
+  genrl::pdl_sync();
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long r = i / cols; const int c = (int)(i - r * cols);
+    const float x = src[r * lds + c];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    hi[r * ldd + c] = h; mid[r * ldd + c] = m; lo[r * ldd + c] = __float2bfloat16_rn(r2);
+  }
+}
+
 __global__ void counter_add_kernel(unsigned long long* c, unsigned long long inc) {
   genrl::pdl_sync(); *c += inc; }
 
@@ -1181,6 +1198,13 @@ extern "C" int genrl_gather_rows(void* stream, const void* src, long long lds, i
 extern "C" int genrl_copy2d(void* stream, const void* src, long long lds, int src_dtype, void* dst, long long ldd, int dst_dtype, long long rows,
                             int cols, const float* row_scale) {
   return genrl_gather_rows(stream, src, lds, src_dtype, nullptr, row_scale, dst, ldd, dst_dtype, rows, cols, 0);
+}
+
+extern "C" int genrl_split3_bf16(void* stream, const float* src, long long lds, void* hi, void* mid, void* lo, long long ldd, long long rows, int cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  const unsigned grid = (unsigned)std::min<long long>((rows * cols + 255) / 256, 148 * 32);
+  genrl::launch_pdl(split3_bf16_kernel, grid, 256, 0, ST(stream), src, lds, (__nv_bfloat16*)hi, (__nv_bfloat16*)mid, (__nv_bfloat16*)lo, ldd, rows, cols);
+  return check_launch("split3_bf16");
 }
 
 extern "C" int genrl_fill_normal(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset,

@@ -165,8 +165,35 @@ def gemm(a, w, out=None, bias=None, trans_a=False, trans_w=False, accumulate=Fal
         out_dtype = out_dtype or a.dtype
         out = empty_act(M, N, a.device, out_dtype)
     _check(out, "gemm C")
+    if a.dtype == torch.float32 and out.dtype == torch.float32 and FP32_TC and M * N * K >= FP32_TC_MIN_WORK:
+        return _gemm_fp32_x3(a, w, out, bias, trans_a, trans_w, accumulate, M, N, K)
     lib.genrl_gemm(_st(), M, N, K, _p(a), _ld(a), int(trans_a), _p(w), _ld(w), int(trans_w), _CODE[a.dtype], _p(out), _ld(out),
                    _CODE[out.dtype], _p(bias), int(accumulate))
+    return out
+
+
+# fp32 parity mode on the tensor cores: each fp32 operand is split into three bf16 terms (8 + 8 + 8 significant bits) and the six products
+# a_i w_j with i + j <= 2 are accumulated in fp32 by the tcgen05 GEMM (smallest terms first).  Relative error ~2^-22 of |a||w|, the same
+# order as the fp32 FFMA kernel's accumulation-order noise, at a sixth of the bf16 rate instead of the SIMT kernel's ~7 TFLOP/s.
+FP32_TC = __import__("os").environ.get("GENRL_FP32_TC", "1") != "0"
+FP32_TC_MIN_WORK = 1 << 24
+
+
+def _split3(t):
+    rows, cols = t.shape
+    ld = _pad8(cols)
+    buf = torch.zeros(3, rows, ld, device=t.device, dtype=torch.bfloat16) if ld != cols else torch.empty(3, rows, ld, device=t.device, dtype=torch.bfloat16)
+    lib.genrl_split3_bf16(_st(), _p(t), _ld(t), buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), ld, rows, cols)
+    return [buf[i][:, :cols] for i in range(3)]
+
+
+def _gemm_fp32_x3(a, w, out, bias, trans_a, trans_w, accumulate, M, N, K):
+    a3, w3 = _split3(a), _split3(w)
+    first = True
+    for i, j in ((0, 2), (2, 0), (1, 1), (0, 1), (1, 0), (0, 0)):
+        lib.genrl_gemm(_st(), M, N, K, _p(a3[i]), _ld(a3[i]), int(trans_a), _p(w3[j]), _ld(w3[j]), int(trans_w), BF16, _p(out), _ld(out), F32,
+                       _p(bias) if first else None, int(accumulate or not first))
+        first = False
     return out
 
 

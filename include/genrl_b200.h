@@ -33,6 +33,10 @@ int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, 
 int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, int transW, void* C,
                     long long ldc, int c_dtype, const float* bias);
 
+/* fp32 parity mode on the tensor cores ("bf16x3"): x = hi + mid + lo with three bf16 terms (24 significant bits); the host side runs the six
+ * products a_i w_j, i + j <= 2, on the bf16 tcgen05 GEMM with fp32 accumulation into C. */
+int genrl_split3_bf16(void* stream, const float* src, long long lds, void* hi, void* mid, void* lo, long long ldd, long long rows, int cols);
+
 /* Linear + LayerNorm(+SiLU) fused (bf16, N multiple of 128 up to 1024): the N/128 column-tile CTAs of a row stripe form a thread-block
  * cluster and merge their per-row (mean, M2) partials through distributed shared memory.  Replaces Linear -> NormLayer -> act
  * (dreamer_utils.py:738-744, :339-346).  pre is kept for the backward pass; stats[M][2] = (mean, rstd). */

@@ -541,3 +541,25 @@ def test_gemm_pair_2cta(tw, M, N, K):
     for _ in range(3):
         out2 = ops.gemm_pair(a, w, bias=bias, trans_w=tw, out_dtype=torch.float32)
     close(out2, ref, rtol=2e-3, atol=2e-2, msg="pair gemm repeat")
+
+
+@pytest.mark.parametrize("ta,tw,M,N,K,acc", [(False, False, 300, 256, 512, False), (False, True, 2400, 1024, 1034, False), (True, True, 384, 520, 2400, True),
+                                             (False, False, 64, 1024, 2048, False)])
+def test_gemm_fp32_on_tensor_cores_bf16x3(ta, tw, M, N, K, acc):
+    """fp32 parity mode above 2^24 MACs: three-term bf16 split of both operands, six tcgen05 products accumulated in fp32 — against a float64
+    matmul the error must stay at the fp32 level (1e-6 of the operand scale x sqrt(K)), i.e. what the FFMA kernel gives"""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    w = torch.randn((K, N) if tw else (N, K), generator=g)
+    bias = None if acc else torch.randn(N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    ref = (a.t() if ta else a).double() @ (w if tw else w.t()).double() + (c0.double() if acc else bias.double())
+    out = c0.clone().to(DEV) if acc else None
+    with ops.use_dtype(torch.float32):
+        assert M * N * K >= ops.FP32_TC_MIN_WORK and ops.FP32_TC
+        res = ops.gemm(a.to(DEV), w.to(DEV), out=out, bias=None if acc else bias.to(DEV), trans_a=ta, trans_w=tw, accumulate=acc)
+    err = float((res.double().cpu() - ref).abs().max())
+    assert err <= 4e-6 * math.sqrt(K) * 4.0, f"max abs err {err:.3e}"
+    simt_like = (a.t() if ta else a) @ (w if tw else w.t())          # torch fp32 on CPU as the yardstick
+    err_ref = float((simt_like.double() + (c0.double() if acc else bias.double()) - ref).abs().max())
+    assert err <= 8 * err_ref + 1e-5, (err, err_ref)

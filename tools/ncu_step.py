@@ -6,7 +6,7 @@ import bench
 from genrl_b200.agent.genrl import GenRLAgent
 
 class A: pass
-args = A(); args.batch, args.length, args.horizon, args.action_dim = 50, 48, 15, 10
+args = A(); args.batch, args.length, args.horizon, args.action_dim, args.sequence, args.preset = 50, 48, 15, 10, "S2", "c2"
 precision = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 cfg, obs_space, act_spec = bench.make_cfg(args, "cuda:0", precision)
 torch.manual_seed(1)

@@ -28,10 +28,10 @@ for name, v in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:40]:
     n = max(v["n"], 1)
     print(f"{v['us']/1e3:9.3f} ms  {100*v['us']/tot:5.1f}%  {v['n']:5d} launches  {v['us']/n:9.1f} us avg  dram rd {v['rd']/n/1e6:8.2f} MB wr {v['wr']/n/1e6:8.2f} MB /launch  {name}")
 if len(sys.argv) > 2:
-    g = [v for k, v in agg.items() if "gemm_tc" in k]           # gemm_tc_kernel (128xBN tiles) + gemm_tc_persist_kernel (256x128, large M)
+    g = [v for k, v in agg.items() if any(t in k for t in ("gemm_tc", "gemm_pair", "mlp_chain", "gemm_ln"))]      # the tcgen05 GEMM family
     if g:
         v = {f: sum(x[f] for x in g) for f in ("n", "us", "rd", "wr")}
-        json.dump({"kernel": "gemm_tc_kernel + gemm_tc_persist_kernel (C-ABI genrl_gemm, bf16)", "launches": v["n"], "dram_bytes_per_launch": (v["rd"] + v["wr"]) / max(v["n"], 1),
+        json.dump({"kernel": "tcgen05 GEMM family: gemm_tc_kernel, gemm_pair_kernel, mlp_chain_fwd_kernel, gemm_tc_persist_kernel, gemm_ln_kernel", "launches": v["n"], "dram_bytes_per_launch": (v["rd"] + v["wr"]) / max(v["n"], 1),
                    "dram_read_bytes_per_launch": v["rd"] / max(v["n"], 1), "dram_write_bytes_per_launch": v["wr"] / max(v["n"], 1),
                    "avg_us": v["us"] / max(v["n"], 1), "share_of_kernel_time": v["us"] / tot,
                    "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one eager step"},
