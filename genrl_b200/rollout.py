@@ -76,16 +76,6 @@ def _vec_ok(t):
     return t.data_ptr() % 16 == 0 and (_ld(t) * t.element_size()) % 16 == 0
 
 
-_WGRAD_STREAMS = {}
-
-
-def _wgrad_stream(dev):
-    k = str(dev)
-    if k not in _WGRAD_STREAMS:
-        _WGRAD_STREAMS[k] = torch.cuda.Stream(device=dev)
-    return _WGRAD_STREAMS[k]
-
-
 def _copy(src, dst, accumulate=False):
     lib.genrl_gather_rows(_st(), _p(src), _ld(src), _CODE[src.dtype], None, None, _p(dst), _ld(dst), _CODE[dst.dtype], dst.shape[0], src.shape[1],
                           int(accumulate))
@@ -228,6 +218,8 @@ class _Rollout(Function):
             dpre_out = _Slab(1, N, Hd, cd, dev)[0]
             dz = _Slab(1, N, 3 * D, cd, dev)[0]
             dx = _Slab(1, N, Hd, cd, dev)[0]
+            dxh = _Slab(1, N, Hd + D, cd, dev)[0]
+            merged_gru_dgrad = cd == torch.bfloat16 and N >= 1024
             dpre_in = _Slab(1, N, Hd, cd, dev)[0]
             dxin = [_Slab(1, N, SK + A, cd, dev)[0], _Slab(1, N, SK + A, cd, dev)[0]]
             train = H > 0 and dense[0].weight.requires_grad
@@ -255,13 +247,6 @@ class _Rollout(Function):
                     bbuf, _ = ops._grad_buf(lin.bias)
                     lib.genrl_colsum(st, _p(dsl), _ld(dsl), _p(bbuf), dsl.shape[0], A, _CODE[cd])
 
-            # The step kernels of the backward loop run at 2 400 rows and leave most SMs idle, the parameter-gradient GEMMs run over
-            # thousands of rows: the gradients of the LATE half of the steps are computed on a side stream while the loop walks the early
-            # half (the two halves accumulate into the same flat buffers, so the early half waits for the late one).
-            mid = H // 2
-            forked = bool(train and H >= 4 and getattr(policy, "_overlap_wgrad", True) and dev.type == "cuda")
-            main_s = torch.cuda.current_stream()
-            side_s = _wgrad_stream(dev) if forked else None
             have_carry = False
             cur = 0
             for i in range(H, 0, -1):
@@ -295,10 +280,17 @@ class _Rollout(Function):
                 gn = G[1 - cur]
                 lib.genrl_gru_bwd(_st(), _p(gh), D, _p(b["z"][j]), _ld(b["z"][j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D,
                                   _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D, None, None, N, D, _CODE[cd])
-                ops.gemm(dz, w_gru_c[:, :Hd], out=dx, trans_w=True)
-                if i > 1:
-                    ops.gemm(dz, w_gru_c[:, Hd:], out=gn, trans_w=True, accumulate=True)
-                _ln_bwd(dx, b["in_pre"][j], ln_in.weight, ln_in.bias, b["in_st"][j], dpre_in)
+                if i > 1 and merged_gru_dgrad:
+                    # one dgrad GEMM for [x | h] (N = Hd + D: enough 256x256 tiles for the 2-CTA kernel), then the h half joins the fp32 carry
+                    ops.gemm(dz, w_gru_c, out=dxh, trans_w=True)
+                    _copy(dxh[:, Hd:], gn, accumulate=True)
+                    dx_i = dxh[:, :Hd]
+                else:
+                    ops.gemm(dz, w_gru_c[:, :Hd], out=dx, trans_w=True)
+                    if i > 1:
+                        ops.gemm(dz, w_gru_c[:, Hd:], out=gn, trans_w=True, accumulate=True)
+                    dx_i = dx
+                _ln_bwd(dx_i, b["in_pre"][j], ln_in.weight, ln_in.bias, b["in_st"][j], dpre_in)
                 ops.gemm(dpre_in, W(lin_in.weight), out=dxin[cur], trans_w=True)
                 # ---- actor head and trunk (input is sg(feat_{i-1}): no gradient leaves through it) --------------------------------------------
                 e = None if eval_policy else b["eps"][j]
@@ -314,13 +306,8 @@ class _Rollout(Function):
                         ops.gemm(a_dpre[l][j], W(dense[l].weight), out=a_dy[l - 1][j], trans_w=True)
                 have_carry = True
                 cur = 1 - cur
-                if forked and j == mid:
-                    side_s.wait_stream(main_s)
-                    with torch.cuda.stream(side_s):
-                        param_grads(mid, H)
-            main_s.wait_stream(side_s) if forked else None
-            if train and H > 0:
-                param_grads(0, mid if forked else H)
+            if train:
+                param_grads(0, H)
         return (None,) * (7 + ctx.n_params)
 
 
