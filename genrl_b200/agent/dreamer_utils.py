@@ -635,7 +635,7 @@ class Optimizer:
 
     def reduce(self, params):
         """data parallel: average the gradients of the groups of `params` now, on the current stream (no-op on one GPU)"""
-        if self.allreduce is not None:
+        if self.allreduce is not None and _EARLY_REDUCE:
             self.store.reduce(self.store.groups_of(list(params)), self.allreduce)
 
     def apply(self, loss, params, active=None):
@@ -651,6 +651,7 @@ class Optimizer:
 
 
 _SIDE_STREAMS = {}
+_EARLY_REDUCE = __import__("os").environ.get("GENRL_DP_EARLY", "1") != "0"
 
 
 def side_stream(device, index=0):
