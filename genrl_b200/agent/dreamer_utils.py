@@ -651,7 +651,10 @@ class Optimizer:
 
 
 _SIDE_STREAMS = {}
-_EARLY_REDUCE = __import__("os").environ.get("GENRL_DP_EARLY", "1") != "0"
+# Data parallel: issue a finished group's gradient all-reduce on the side stream right away (beside the other stream's backward).  Measured on
+# 8 B200s (profiles/r02_notes.md §11): 24.69 ms with it, 24.39 ms without — the NCCL kernels take SMs from the persistent one-CTA-per-SM
+# kernels they run beside — so it is opt-in.
+_EARLY_REDUCE = __import__("os").environ.get("GENRL_DP_EARLY", "0") == "1"
 
 
 def side_stream(device, index=0):
