@@ -464,31 +464,57 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
     n = 3
     agg = cupti_kernels(lambda i: step(devb[i % nb], i), n)
     total_us = sum(v[1] for v in agg.values())
+    # 2b. the same with the two-stream overlap off: every kernel runs alone, so its duration is the kernel's own (in the overlapped step a
+    #     GEMM's duration also contains the time it shares the SMs with the other stream's kernels)
+    agg_alone = None
+    if getattr(agent.cfg, "overlap_streams", False):
+        ov = agent.cfg.overlap_streams
+        agent.cfg.overlap_streams = False
+        for beh in (getattr(agent, "_acting_behavior", None), getattr(agent, "_imag_behavior", None)):
+            if beh is not None and getattr(beh, "cfg", None) is not agent.cfg:
+                beh.cfg.overlap_streams = False
+        saved_graphs, agent._graphs = agent._graphs, {}
+        for i in range(4):
+            step(devb[i % nb], i)
+        agg_alone = cupti_kernels(lambda i: step(devb[i % nb], i), n)
+        agent.cfg.overlap_streams = ov
+        agent._graphs = saved_graphs
+        for i in range(2):
+            step(devb[i % nb], i)
     breakdown = {k: {"ms_per_step": v[1] / n / 1e3, "launches_per_step": v[0] / n, "avg_us": v[1] / v[0], "share_of_kernel_time": v[1] / total_us}
                  for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]}
     breakdown["_total"] = {"kernel_ms_per_step": total_us / n / 1e3, "launches_per_step": sum(v[0] for v in agg.values()) / n,
                            "step_ms": ms_step, "source": f"CUPTI (torch.profiler) over {n} graph-replayed steps"}
     fam = lambda *pats: [sum(v[0] for k, v in agg.items() if any(p in k for p in pats)), sum(v[1] for k, v in agg.items() if any(p in k for p in pats))]
-    g_l, g_us = fam("gemm_tc_kernel", "gemm_tc_persist_kernel", "gemm_ln_kernel", "gemm_simt_kernel", "gemm_pair_kernel", "mlp_chain_fwd_kernel")
+    GEMM_FAMILY = ("gemm_tc_kernel", "gemm_tc_persist_kernel", "gemm_ln_kernel", "gemm_simt_kernel", "gemm_pair_kernel", "mlp_chain_fwd_kernel")
+    g_l, g_us = fam(*GEMM_FAMILY)
+    alone_us = sum(v[1] for k, v in agg_alone.items() if any(p in k for p in GEMM_FAMILY)) if agg_alone else None
     roof = None
     if g_us > 0:
-        achieved = counts["gemm_flops"] * n / (g_us * 1e-6) / 1e12
+        in_step = counts["gemm_flops"] * n / (g_us * 1e-6) / 1e12
+        achieved = counts["gemm_flops"] * n / (alone_us * 1e-6) / 1e12 if alone_us else in_step
         peak = pk["tf_sustained"] if bf16 else 75.0
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if bf16 and os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")      # ncu dram__bytes_read+write, mean over the step's GEMM launches
         roof = {"kernel": "tcgen05 GEMM family: gemm_tc_kernel (128xBN), gemm_pair_kernel (2-CTA 256x256), mlp_chain_fwd_kernel (Linear+LN chains), "
                           "gemm_tc_persist_kernel, gemm_ln_kernel" if bf16 else "gemm_simt_kernel (fp32 parity mode)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": (pk["source"] + " bf16 sustained") if bf16 else "nominal fp32 FFMA",
-                "share_of_step": g_us / total_us, "launch_avg_us": g_us / g_l, "launches_per_step": g_l / n,
+                "achieved_in_overlapped_step": in_step, "frac_in_overlapped_step": in_step / peak,
+                "share_of_step": g_us / total_us, "launch_avg_us": (alone_us or g_us) / g_l, "launches_per_step": g_l / n,
                 "algorithmic_flops_per_launch": counts["gemm_flops"] * n / g_l, "algorithmic_flops_per_step": counts["gemm_flops"],
-                "method": f"sum of 2MNK over the step's {counts['gemm_calls']} GEMM calls / sum of their CUPTI kernel durations inside {n} graph-replayed steps"}
+                "method": f"sum of 2MNK over the step's {counts['gemm_calls']} GEMM / chain calls / sum of their CUPTI kernel durations over {n} graph-replayed "
+                          "steps with the two-stream overlap off (each kernel alone on the GPU); *_in_overlapped_step: the same inside the timed two-stream steps"}
     out = {"roofline": roof, "kernel_breakdown": breakdown}
     # conv stacks
     frames = args.batch * args.length
     f_fwd, f_wg = conv_algorithmic_flops(frames)
+    src = agg_alone or agg               # kernel durations with each kernel alone on the GPU when that pass ran
+    fam = lambda *pats: [sum(v[0] for k, v in src.items() if any(p in k for p in pats)), sum(v[1] for k, v in src.items() if any(p in k for p in pats))]
     c_l, c_us = fam("conv_fwd_kernel")
     w_l, w_us = fam("conv_wgrad_kernel")
     if bf16 and c_us > 0 and w_us > 0:
