@@ -42,7 +42,6 @@ def parse():
                     help="BASELINE.json configs: c2 stickman (default) | c4 kitchen (A = 9, extra low-dimensional `state` observation key) | "
                          "c5 large RSSM per-GPU shard (deter = hidden = 4096, stoch 48x48, batch 16x64, imag_horizon 32)")
     ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: total sequences, split evenly over the ranks (default: --batch per rank, weak scaling)")
-    ap.add_argument("--rollout-streams", type=int, default=1, help="row chunks of the imagination rollout enqueued on separate CUDA streams (measured: 2-4 chunks are 9-11 % slower, profiles/r02_notes.md)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"], help="--impl reference: host cores (default) or torch-eager on the GPU")
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference --ref-device cuda: fp16 autocast (the reference's precision: 16)")
     ap.add_argument("--ref-batch", type=int, default=0, help="--impl reference: sample size in sequences (default REF_SAMPLE_B)")
@@ -238,7 +237,6 @@ def run_native(args):
     cfg, obs_space, act_spec = make_cfg(args, dev, args.precision)
     cfg.cuda_graph = not args.eager
     cfg.overlap_streams = not args.no_overlap
-    cfg.rollout_streams = 1 if args.no_overlap else args.rollout_streams
     torch.manual_seed(1)
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):

@@ -449,42 +449,11 @@ class WorldModel(Module):
         return model_loss, last_state, outs, metrics
 
     def imagine(self, policy, start, is_terminal, horizon, task_cond=None, eval_policy=False):
-        """reference dreamer.py:254-287.
-
-        Every op of the rollout is row-wise, and at N = B*T = 2 400 rows each of its ~45 kernels per step is latency-bound (a
-        2400x1024x1024 GEMM is one wave of CTAs at half the per-SM tensor rate, the row kernels move a few MB).  With
-        cfg.rollout_streams = S > 1 the rows are split into S contiguous chunks whose rollouts are enqueued on S CUDA streams: the
-        chains are independent, so their kernels overlap on the SMs (autograd replays each chain's backward on its own stream too).
-        Off in tape-replay parity mode (the reference's draws come in whole-batch order)."""
+        """reference dreamer.py:254-287"""
         assert task_cond is None
         flatten = lambda x: x.reshape([-1] + list(x.shape[2:]))
         start = {k: flatten(v) for k, v in start.items()}
-        N = start["deter"].shape[0]
-        chunks = int(getattr(self.cfg, "rollout_streams", 1) or 1)
-        if chunks > 1 and isinstance(ops.noise, ops.PhiloxNoise) and start["deter"].is_cuda and N >= 256 * chunks and horizon > 0:
-            main = torch.cuda.current_stream()
-            streams = [main] + [common.side_stream(self.device, 1 + i) for i in range(chunks - 1)]
-            bounds = [N * i // chunks // 8 * 8 for i in range(chunks)] + [N]
-            outs = []
-            for i, st in enumerate(streams):
-                part = {k: v[bounds[i]:bounds[i + 1]] for k, v in start.items()}
-                if st is not main:
-                    st.wait_stream(main)
-                with torch.cuda.stream(st):
-                    outs.append(self._imagine_rows(policy, part, horizon, eval_policy))
-            for st in streams[1:]:
-                main.wait_stream(st)
-            self._rollout_side = streams[1:]        # autograd replays each chunk's backward on its stream: join_rollout() after backward
-            return {k: torch.cat([o[k] for o in outs], 1) for k in outs[0]}
         return self._imagine_rows(policy, start, horizon, eval_policy)
-
-    def join_rollout(self):
-        """after a backward through a row-chunked rollout: the chunk backward chains ran on the side streams and wrote parameter
-        gradients straight into the flat buffers (nothing autograd would synchronise on) -> make the current stream wait for them"""
-        main = torch.cuda.current_stream()
-        for st in getattr(self, "_rollout_side", ()):
-            main.wait_stream(st)
-        self._rollout_side = ()
 
     def _imagine_rows(self, policy, start, horizon, eval_policy=False):
         from .. import rollout
@@ -606,7 +575,6 @@ class ActorCritic(Module):
                     self.critic_opt.backward(critic_loss)
                     self.critic_opt.reduce(self.critic.parameters())      # collective beside the actor's backward
                 self.actor_opt.backward(actor_loss)
-                world_model.join_rollout()
                 dg.flush()
                 main.wait_stream(side)
                 metrics.update(self.actor_opt.apply(actor_loss, self.actor.parameters()))
@@ -620,7 +588,6 @@ class ActorCritic(Module):
                 target, mets2, baseline = self.target(seq)
                 actor_loss, mets3 = self.actor_loss(seq, target, baseline)
                 self.actor_opt.backward(actor_loss)
-                world_model.join_rollout()
                 dg.flush()
                 metrics.update(self.actor_opt.apply(actor_loss, self.actor.parameters()))
             with common.RequiresGrad(self.critic):

@@ -253,48 +253,6 @@ def test_direct_wm_calls_of_train_py_work_without_a_prior_update():
     ops.set_noise(ops.PhiloxNoise(0))
 
 
-def test_row_chunked_rollout_on_two_streams():
-    """cfg.rollout_streams = 2: the imagination rollout of the two halves of the rows runs on two streams (eager and graph-captured).
-    The chunks draw from different Philox offsets than the whole-batch rollout, so values are compared where they are noise-free
-    (start entries, shapes) or statistically (losses of several updates stay within a few percent of the single-stream run)."""
-    from genrl_b200 import ops
-    from genrl_b200.agent.genrl import GenRLAgent
-    from genrl_b200.config import tiny_overrides
-    from genrl_b200.synthetic import synthetic_batch
-    B, T, A, H = 16, 32, 6, 5            # N = 512 rows: two chunks of 256
-    hist = {}
-    for streams, graph in ((1, False), (2, False), (2, True)):
-        cfg = genrl_config(device=DEV, precision=32, batch_size=B, batch_length=T, imag_horizon=H, **tiny_overrides())
-        cfg.rollout_streams, cfg.cuda_graph, cfg.overlap_streams = streams, graph, True
-        obs_space, act_spec = make_specs(action_dim=A, clip_dim=32)
-        torch.manual_seed(1)
-        agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
-        ops.set_noise(ops.PhiloxNoise(21))
-        data = {k: v.to(DEV) for k, v in synthetic_batch(B, T, A, clip_dim=32, seed=8, resets=0.05).items()}
-        out = []
-        for i in range(4):
-            state, outputs, metrics = agent.update_wm(data, i)
-            start, metrics = agent.update_acting_behavior(state, outputs, metrics, data)
-            out.append({k: float(torch.as_tensor(metrics[k]).float().cpu().reshape(-1)[0]) for k in
-                        ("model_loss", "actor_loss", "critic_loss", "actor_grad_norm", "critic_grad_norm", "actor_ent", "critic_target")})
-            assert all(np.isfinite(v) for v in out[-1].values()), (streams, graph, out[-1])
-        hist[(streams, graph)] = out
-        if streams == 2 and not graph:
-            with torch.no_grad(), agent._ctx():
-                post = {k: v.detach() for k, v in outputs["post"].items()}
-                seq = agent.wm.imagine(agent._acting_behavior.actor, post, None, H)
-                assert seq["feat"].shape == (H + 1, B * T, 128) and seq["action"].shape == (H + 1, B * T, A)
-                assert torch.equal(seq["stoch"][0].float(), post["stoch"].reshape(B * T, 8, 8).float())
-                assert float(seq["stoch"].float().sum(-1).min()) == 1.0
-    ref = hist[(1, False)]
-    for key in ((2, False), (2, True)):
-        for a, b in zip(ref, hist[key]):
-            assert abs(a["model_loss"] - b["model_loss"]) <= 1e-4 * abs(a["model_loss"])       # the world-model update is untouched
-            for k in ("critic_loss", "actor_ent"):
-                assert abs(a[k] - b[k]) <= 5e-2 * max(1.0, abs(a[k])), (key, k, a[k], b[k])
-    ops.set_noise(ops.PhiloxNoise(0))
-
-
 def test_kitchen_shaped_agent_full_conv_stack_bf16_tracks_fp32():
     """BASELINE configs[3]: kitchen has A = 9 and an extra low-dimensional `state` observation key that the GenRL encoder ignores
     (conf/env/dmc_pixels.yaml: mlp_keys '$^').  Full-size conv stacks (depth 48, 64x64), small batch: the bf16 tensor-core path

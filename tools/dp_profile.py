@@ -19,7 +19,7 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 class A: pass
 args = A(); args.batch, args.length, args.horizon, args.action_dim, args.sequence, args.preset = 50, 48, 15, 10, "S2", "c2"
 cfg, obs_space, act_spec = bench.make_cfg(args, dev, 16)
-cfg.cuda_graph, cfg.overlap_streams, cfg.rollout_streams = True, True, 1
+cfg.cuda_graph, cfg.overlap_streams = True, True
 torch.manual_seed(1)
 with contextlib.redirect_stdout(io.StringIO()):
     agent = GenRLAgent(name="genrl", cfg=cfg, obs_space=obs_space, act_spec=act_spec)
