@@ -4,7 +4,9 @@
 // Each forward has a hand-written backward (no autograd inside the library).
 #include "common.cuh"
 #include "rowops_fast.cuh"
+#include "ln_pipe.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace genrl {
 
@@ -902,12 +904,52 @@ static int num_sms_rows() {
   return n;
 }
 static inline int ln_lpr(int D, int nch) { int l = 1; while (l * 8 * nch < D) l *= 2; return l; }
+// the bulk-copy pipelines of ln_pipe.cuh pay from ~4 row tiles per SM (below that the register kernels' finer grid wins); GENRL_LN_PIPE=0 turns
+// them off (A/B measurements)
+static bool ln_pipe_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GENRL_LN_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+static bool ln_pipe_fwd_on() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GENRL_LN_PIPE_FWD"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+// launchers of the compile-time-geometry pipelines: one function-local flag per instantiation for the opt-in shared-memory size
+template <typename T, int LPR, int CPL, bool COLG>
+static void ln_bwd_pipe_launch(cudaStream_t st, const T* dy, long long lddy, const T* x, long long ldx, const float* gamma, const float* beta, const float* stats,
+                               int act, T* dx, long long lddx, float* dgamma, float* dbeta, float* dlb, long long M) {
+  using G = LnpGeom<T, LPR, CPL>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(ln_bwd_pipe_kernel<T, LPR, CPL, COLG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::BWD_SMEM); attr_set = true; }
+  const long long ntiles = (M + G::R - 1) / G::R;
+  genrl::launch_pdl(ln_bwd_pipe_kernel<T, LPR, CPL, COLG>, (int)std::min<long long>(ntiles, (long long)LNP_BLOCKS_PER_SM * num_sms_rows()), LNP_THREADS, G::BWD_SMEM, st, dy, lddy, x, ldx, gamma, beta,
+                    stats, act, dx, lddx, dgamma, dbeta, dlb, M);
+}
+template <typename T, int LPR, int CPL>
+static void ln_fwd_pipe_launch(cudaStream_t st, const T* x, long long ldx, const float* gamma, const float* beta, float eps, int act, T* y, long long ldy,
+                               float* stats, long long M) {
+  using G = LnpGeom<T, LPR, CPL>;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(ln_fwd_pipe_kernel<T, LPR, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::FWD_SMEM); attr_set = true; }
+  const long long ntiles = (M + G::FR - 1) / G::FR;
+  genrl::launch_pdl(ln_fwd_pipe_kernel<T, LPR, CPL>, (int)std::min<long long>(ntiles, (long long)LNP_BLOCKS_PER_SM * num_sms_rows()), LNP_THREADS, G::FWD_SMEM, st, x, ldx, gamma, beta, eps, act, y, ldy,
+                    stats, M);
+}
+// eligible when the width has an instantiation and there are at least ~4 row tiles per SM (16 384 elements per tile)
+template <typename T> static bool ln_pipe_ok(long long M, int D) {
+  int lpr, cpl;
+  return ln_pipe_enabled() && lnp_geom(D, &lpr, &cpl) && M * D >= (long long)4 * num_sms_rows() * (sizeof(T) == 2 ? 16384 : 8192);
+}
 
 extern "C" int genrl_ln_act_fwd(void* stream, const void* x, long long ldx, const float* gamma, const float* beta, float eps, int act,
                                 void* y, long long ldy, float* stats, long long M, int D, int dtype) {
   if (M <= 0) return 0;
   DISPATCH_T(dtype, {
-    if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(y, ldy) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+    if (ln_pipe_fwd_on() && ln_pipe_ok<T>(M, D) && vec_ok<T>(x, ldx) && vec_ok<T>(y, ldy)) {
+      LNP_DISPATCH(D, (ln_fwd_pipe_launch<T, LPR, CPL>(ST(stream), (const T*)x, ldx, gamma, beta, eps, act, (T*)y, ldy, stats, M)));
+    } else if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(y, ldy) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       const int nch = D <= 384 ? 6 : 4;
       const int lpr = ln_lpr(D, nch);
       const long long rpb = 8 * (32 / lpr);
@@ -928,7 +970,16 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
   GENRL_REQUIRE(3 * D * 4 <= 200 * 1024, "ln_act_bwd: D too large");
   size_t smem = (size_t)3 * D * sizeof(float);
   DISPATCH_T(dtype, {
-    if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
+    if (ln_pipe_ok<T>(M, D) && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && (reinterpret_cast<uintptr_t>(stats) & 7) == 0) {
+      // large row counts: bulk-copy pipeline through shared memory (ln_pipe.cuh), one persistent 512-thread block per SM
+      if (dgamma || dlin_bias) {
+        LNP_DISPATCH(D, (ln_bwd_pipe_launch<T, LPR, CPL, true>(ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, dgamma, dbeta,
+                                                               dlin_bias, M)));
+      } else {
+        LNP_DISPATCH(D, (ln_bwd_pipe_launch<T, LPR, CPL, false>(ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, (float*)nullptr,
+                                                                (float*)nullptr, (float*)nullptr, M)));
+      }
+    } else if (D % 8 == 0 && D <= 1024 && vec_ok<T>(x, ldx) && vec_ok<T>(dy, lddy) && vec_ok<T>(dx, lddx) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       if (dgamma || dlin_bias) {
         // one pass: dx and the parameter gradients (narrow rows use 2 chunks per lane: 128 registers, two blocks per SM)
         const int nch = D <= 384 ? 2 : 4;
@@ -951,8 +1002,12 @@ extern "C" int genrl_ln_act_bwd(void* stream, const void* dy, long long lddy, co
         const int lpr = ln_lpr(D, nch);
         const long long rpb = 8 * (32 / lpr);
         const int grid = (int)std::min<long long>((M + rpb - 1) / rpb, 148 * 16);
-        if (nch == 6) genrl::launch_pdl(ln_bwd_fast_kernel<T, 6>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
-        else genrl::launch_pdl(ln_bwd_fast_kernel<T, 4>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+        const long long rows_wave4 = (long long)num_sms_rows() * 5 * 4 * (32 / lpr);      // rows one wave of the 4-warp variant covers
+        if (nch == 6) genrl::launch_pdl(ln_bwd_fast_kernel<T, 6, 8>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
+        else if (M > (long long)num_sms_rows() * 2 * rpb && M <= rows_wave4)
+          genrl::launch_pdl(ln_bwd_fast_kernel<T, 4, 4>, (int)((M + rpb / 2 - 1) / (rpb / 2)), 128, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act,
+                            (T*)dx, lddx, M, D, lpr);
+        else genrl::launch_pdl(ln_bwd_fast_kernel<T, 4, 8>, grid, 256, 0, ST(stream), (const T*)dy, lddy, (const T*)x, ldx, gamma, beta, stats, act, (T*)dx, lddx, M, D, lpr);
       }
     } else {
       if (smem > 48 * 1024) cudaFuncSetAttribute(ln_act_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1021,7 +1076,7 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
         (!dhprev || vec_ok<float>(dhprev, lddhp)) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       if (D == 1024)
         genrl::launch_pdl(gru_bwd_row1024_kernel<T>, (int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
-                                                                                               (T*)dz, lddz, dhprev, lddhp, M);
+                                                                                               (T*)dz, lddz, dhprev, lddhp, M, (const T*)nullptr, 0LL, (const T*)nullptr, 0LL);
       else
         genrl::launch_pdl(gru_bwd_fast_kernel<T>, row_grid(M, 148 * 16), 256, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
                                                                              dhprev, lddhp, M, D);
@@ -1032,6 +1087,23 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
     }
   });
   return check_launch("gru_bwd");
+}
+
+// frozen-weights GRU backward at D = 1024 whose incoming gradient is dh + e1 + e2 (e1 / e2 optional, activation dtype).  Returns 2 when the
+// shape / alignment is not eligible (the caller then sums the contributions itself and calls genrl_gru_bwd).
+extern "C" int genrl_gru_bwd_sum(void* stream, const float* dh, long long lddh, const void* e1, long long lde1, const void* e2, long long lde2,
+                                 const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
+                                 const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp, long long M, int D, int dtype) {
+  if (M <= 0) return 0;
+  if (D != 1024) return 2;
+  DISPATCH_T(dtype, {
+    if (!(vec_ok<T>(z, ldz) && vec_ok<T>(dz, lddz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(dh, lddh) && (!dhprev || vec_ok<float>(dhprev, lddhp)) &&
+          (!e1 || vec_ok<T>(e1, lde1)) && (!e2 || vec_ok<T>(e2, lde2)) && f32_vec_ok(gamma) && f32_vec_ok(beta)))
+      return 2;
+    genrl::launch_pdl(gru_bwd_row1024_kernel<T>, (int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
+                      (T*)dz, lddz, dhprev, lddhp, M, (const T*)e1, lde1, (const T*)e2, lde2);
+  });
+  return check_launch("gru_bwd_sum");
 }
 
 extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const float* noise, unsigned long long seed, unsigned long long offset,

@@ -107,15 +107,17 @@ __global__ void __launch_bounds__(256, (FAST_NCH == 4 ? 4 : 2)) ln_fwd_fast_kern
 }
 
 // ---- LayerNorm (+SiLU) backward, row pass: dx only ------------------------------------------------------------------
-template <typename T, int FAST_NCH>
-__global__ void __launch_bounds__(256, 2) ln_bwd_fast_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
+// WPB = warps per block: 8 (two blocks per SM) for large row counts; 4 with five blocks per SM (20 resident rows-in-flight per SM at one
+// row per warp) so that the 2 400-row launches of the imagination rollout's reverse loop are ONE wave instead of 296 + 4 blocks.
+template <typename T, int FAST_NCH, int WPB>
+__global__ void __launch_bounds__(WPB * 32, (WPB == 8 ? 2 : 5)) ln_bwd_fast_kernel(const T* __restrict__ dy, long long lddy, const T* __restrict__ x, long long ldx,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const float* __restrict__ stats, int act, T* __restrict__ dx, long long lddx,
                                                           long long M, int D, int lpr) {
   genrl::pdl_sync();
   const int lane = threadIdx.x & 31, sub = lane % lpr, rwi = lane / lpr, rpw = 32 / lpr;
-  const long long wstride = (long long)gridDim.x * 8 * rpw;
-  for (long long base = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * rpw; base < M; base += wstride) {
+  const long long wstride = (long long)gridDim.x * WPB * rpw;
+  for (long long base = ((long long)blockIdx.x * WPB + (threadIdx.x >> 5)) * rpw; base < M; base += wstride) {
     const long long row = base + rwi;
     const bool valid = row < M;
     const float mean = valid ? stats[row * 2] : 0.f, rstd = valid ? stats[row * 2 + 1] : 0.f;
@@ -498,7 +500,10 @@ template <typename T>
 __global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __restrict__ dh, long long lddh, const T* __restrict__ z, long long ldz,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
-                                                              T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M) {
+                                                              T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M,
+                                                              const T* __restrict__ e1, long long lde1, const T* __restrict__ e2, long long lde2) {
+  // e1 / e2 (optional, activation dtype): further contributions to d loss / d h summed on the fly (the rollout's feat-slice gradient and the
+  // h half of the previous step's GRU dgrad) instead of two accumulate-copy launches per step
   genrl::pdl_sync();
   constexpr int D = 1024, D3 = 3072;
   __shared__ float red[2][4];
@@ -511,6 +516,12 @@ __global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __res
     float a[8], b[8], c[8], r[8], cand[8], u[8], pc[8], xr[8], xc[8], xu[8], h[8], g[8];
     V8<T>::load(zr_ + j, a); V8<T>::load(zr_ + D + j, b); V8<T>::load(zr_ + 2 * D + j, c);
     ldf8(hprev + row * ldh + j, h); ldf8(dh + row * lddh + j, g);
+    if (e1) { float t[8]; V8<T>::load(e1 + row * lde1 + j, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += t[k]; }
+    if (e2) { float t[8]; V8<T>::load(e2 + row * lde2 + j, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += t[k]; }
     gru_gate8<(sizeof(T) == 2)>(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll

@@ -207,9 +207,6 @@ class _Rollout(Function):
                 dstoch = dstoch if dstoch.stride(-1) == 1 else dstoch.contiguous()
             if dent is not None:
                 dent = dent.contiguous().float()
-            # slabs the deferred parameter gradients read after the loop
-            a_dy = [_Slab(H, N, U, cd, dev) for _ in range(L)]
-            a_dpre = [_Slab(H, N, U, cd, dev) for _ in range(L)]
             dout2c = _Slab(H, N, 2 * A, cd, dev, zero=True)
             G = [torch.zeros(N, D, device=dev, dtype=torch.float32), torch.empty(N, D, device=dev, dtype=torch.float32)]     # d loss / d deter_i
             dlogit = torch.empty(N, SK, device=dev, dtype=torch.float32)
@@ -218,34 +215,52 @@ class _Rollout(Function):
             dpre_out = _Slab(1, N, Hd, cd, dev)[0]
             dz = _Slab(1, N, 3 * D, cd, dev)[0]
             dx = _Slab(1, N, Hd, cd, dev)[0]
-            dxh = _Slab(1, N, Hd + D, cd, dev)[0]
+            dxh = [_Slab(1, N, Hd + D, cd, dev)[0], _Slab(1, N, Hd + D, cd, dev)[0]]
+            fold_ok = D == 1024 and cd == torch.bfloat16
+            pending_h = None
             merged_gru_dgrad = cd == torch.bfloat16 and N >= 1024
             dpre_in = _Slab(1, N, Hd, cd, dev)[0]
-            dxin = [_Slab(1, N, SK + A, cd, dev)[0], _Slab(1, N, SK + A, cd, dev)[0]]
+            # d loss / d [stoch_{i-1} | action_i] of EVERY step: the stoch part is the next iteration's carry, the action part is all the actor's
+            # backward needs, so the actor's whole backward runs ONCE over the H*N rows after the loop (below)
+            dxin = _Slab(H, N, SK + A, cd, dev)
             train = H > 0 and dense[0].weight.requires_grad
 
-            def param_grads(lo, hi):
-                """actor parameter gradients over the rollout steps lo..hi-1: one wgrad GEMM and one column pass per layer (the slabs are
-                contiguous, so the rows of several steps are one matrix)"""
+            def actor_backward():
+                """The actor reads sg(feat_{i-1}) (dreamer.py:265): no gradient leaves its trunk, so nothing in the recurrence's reverse loop
+                depends on it.  Its backward of all H steps is therefore ONE pass over the contiguous [H*N, .] slabs: head backward, then per
+                layer one LayerNorm backward (row pass + dgamma / dbeta / dbias column partials in the same launch), one dgrad GEMM and one
+                wgrad GEMM at 36 000 rows — instead of H x (4 + 4 + 2) launches at 2 400 rows."""
                 st = _st()
-                for l in range(L):
-                    X = b["feat"].all(lo, hi) if l == 0 else b["a_y"][l - 1].all(lo, hi)
-                    DP, DY, PRE = a_dpre[l].all(lo, hi), a_dy[l].all(lo, hi), b["a_pre"][l].all(lo, hi)
-                    gbuf, _ = ops._grad_buf(dense[l].weight)
-                    ops.gemm(DP, X, out=gbuf.view(U, -1), trans_a=True, trans_w=True, accumulate=True)
-                    gb, _ = ops._grad_buf(norms[l].weight)
-                    bb, _ = ops._grad_buf(norms[l].bias)
-                    lb = ops._grad_buf(dense[l].bias)[0] if dense[l].bias is not None else None
-                    lib.genrl_ln_colgrad(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(DP), _ld(DP), _p(norms[l].weight), _p(norms[l].bias),
-                                         _p(b["a_st"][l][lo:hi].reshape(-1, 2)), ACT_SILU, _p(gb), _p(bb), _p(lb), DP.shape[0], U, _CODE[cd])
-                XH = b["a_y"][L - 1].all(lo, hi)
-                DO = dout2c.all(lo, hi)
+                M = H * N
+                e = None if eval_policy else b["eps"].reshape(M, A)
+                if e is None:
+                    e = torch.zeros(M, A, device=dev, dtype=torch.float32)
+                DA = dxin.all()[:, SK:]
+                DO = dout2c.all()
+                lib.genrl_actor_head_bwd(st, _p(b["out2"]), 2 * A, _p(e), _p(DA), _ld(DA), _p(dent), 1.0 if dent is not None else 0.0,
+                                         _p(DO), _ld(DO), _CODE[cd], M, A, _CODE[cd])
+                DY = _Slab(1, M, U, cd, dev)[0]
+                DP = _Slab(1, M, U, cd, dev)[0]
+                ops.gemm(DO, w_head, out=DY, trans_w=True)
+                XH = b["a_y"][L - 1].all()
                 for part, lin in ((0, policy._out._out), (1, policy._out._std)):
                     gbuf, _ = ops._grad_buf(lin.weight)
                     dsl = DO[:, part * A:(part + 1) * A]
                     ops.gemm(dsl, XH, out=gbuf.view(A, U), trans_a=True, trans_w=True, accumulate=True)
                     bbuf, _ = ops._grad_buf(lin.bias)
                     lib.genrl_colsum(st, _p(dsl), _ld(dsl), _p(bbuf), dsl.shape[0], A, _CODE[cd])
+                for l in range(L - 1, -1, -1):
+                    PRE = b["a_pre"][l].all()
+                    gb, _ = ops._grad_buf(norms[l].weight)
+                    bb, _ = ops._grad_buf(norms[l].bias)
+                    lb = ops._grad_buf(dense[l].bias)[0] if dense[l].bias is not None else None
+                    lib.genrl_ln_act_bwd(st, _p(DY), _ld(DY), _p(PRE), _ld(PRE), _p(norms[l].weight), _p(norms[l].bias),
+                                         _p(b["a_st"][l].reshape(-1, 2)), ACT_SILU, _p(DP), _ld(DP), _p(gb), _p(bb), _p(lb), M, U, _CODE[cd])
+                    X = b["feat"].all(0, H) if l == 0 else b["a_y"][l - 1].all()
+                    gbuf, _ = ops._grad_buf(dense[l].weight)
+                    ops.gemm(DP, X, out=gbuf.view(U, -1), trans_a=True, trans_w=True, accumulate=True)
+                    if l > 0:
+                        ops.gemm(DP, W(dense[l].weight), out=DY, trans_w=True)
 
             have_carry = False
             cur = 0
@@ -258,10 +273,20 @@ class _Rollout(Function):
                 if dstoch is not None:
                     srcs.append(dstoch[i])
                 if have_carry:
-                    srcs.append(dxin[1 - cur][:, :SK])
+                    srcs.append(dxin[i][:, :SK])
                 gh = G[cur]
+                # further contributions to d loss / d deter_i, summed inside the GRU backward kernel when it can (else by accumulate-copies)
+                extras = []
                 if dfeat is not None:
-                    _copy(dfeat[i][:, SK:], gh, accumulate=True)
+                    extras.append(dfeat[i][:, SK:])
+                if pending_h is not None:
+                    extras.append(pending_h)
+                pending_h = None
+                fold = fold_ok and all(e_.dtype == cd and _vec_ok(e_) for e_ in extras)
+                if not fold:
+                    for e_ in extras:
+                        _copy(e_, gh, accumulate=True)
+                    extras = []
                 if srcs:
                     if K == 32 and len(srcs) <= 2 and all(s_.dtype == cd and _vec_ok(s_) for s_ in srcs) and _vec_ok(dlogit_c):
                         # both contributions summed on the fly, gradient written in the activation dtype: one launch
@@ -278,36 +303,32 @@ class _Rollout(Function):
                     ops.gemm(dpre_out, W(lin_out.weight), out=gh, trans_w=True, accumulate=True)
                 # ---- GRU cell -------------------------------------------------------------------------------------------------------------
                 gn = G[1 - cur]
-                lib.genrl_gru_bwd(_st(), _p(gh), D, _p(b["z"][j]), _ld(b["z"][j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D,
-                                  _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D, None, None, N, D, _CODE[cd])
+                if extras:
+                    e1 = extras[0]
+                    e2 = extras[1] if len(extras) > 1 else None
+                    lib.genrl_gru_bwd_sum(_st(), _p(gh), D, _p(e1), _ld(e1), _p(e2), _ld(e2) if e2 is not None else 0, _p(b["z"][j]), _ld(b["z"][j]),
+                                          _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D, _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D,
+                                          N, D, _CODE[cd])
+                else:
+                    lib.genrl_gru_bwd(_st(), _p(gh), D, _p(b["z"][j]), _ld(b["z"][j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D,
+                                      _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D, None, None, N, D, _CODE[cd])
                 if i > 1 and merged_gru_dgrad:
-                    # one dgrad GEMM for [x | h] (N = Hd + D: enough 256x256 tiles for the 2-CTA kernel), then the h half joins the fp32 carry
-                    ops.gemm(dz, w_gru_c, out=dxh, trans_w=True)
-                    _copy(dxh[:, Hd:], gn, accumulate=True)
-                    dx_i = dxh[:, :Hd]
+                    # one dgrad GEMM for [x | h] (N = Hd + D: enough 256x256 tiles for the 2-CTA kernel); the h half joins the carry inside the
+                    # next iteration's GRU backward (or by an accumulate-copy when that kernel is not eligible)
+                    ops.gemm(dz, w_gru_c, out=dxh[i & 1], trans_w=True)
+                    pending_h = dxh[i & 1][:, Hd:]
+                    dx_i = dxh[i & 1][:, :Hd]
                 else:
                     ops.gemm(dz, w_gru_c[:, :Hd], out=dx, trans_w=True)
                     if i > 1:
                         ops.gemm(dz, w_gru_c[:, Hd:], out=gn, trans_w=True, accumulate=True)
                     dx_i = dx
                 _ln_bwd(dx_i, b["in_pre"][j], ln_in.weight, ln_in.bias, b["in_st"][j], dpre_in)
-                ops.gemm(dpre_in, W(lin_in.weight), out=dxin[cur], trans_w=True)
-                # ---- actor head and trunk (input is sg(feat_{i-1}): no gradient leaves through it) --------------------------------------------
-                e = None if eval_policy else b["eps"][j]
-                if e is None:
-                    e = torch.zeros(N, A, device=dev, dtype=torch.float32)
-                de = None if dent is None else dent[j]
-                lib.genrl_actor_head_bwd(_st(), _p(b["out2"][j]), 2 * A, _p(e), _p(dxin[cur][:, SK:]), _ld(dxin[cur]), _p(de),
-                                         1.0 if de is not None else 0.0, _p(dout2c[j]), _ld(dout2c[j]), _CODE[cd], N, A, _CODE[cd])
-                ops.gemm(dout2c[j], w_head, out=a_dy[L - 1][j], trans_w=True)
-                for l in range(L - 1, -1, -1):
-                    _ln_bwd(a_dy[l][j], b["a_pre"][l][j], norms[l].weight, norms[l].bias, b["a_st"][l][j], a_dpre[l][j])
-                    if l > 0:
-                        ops.gemm(a_dpre[l][j], W(dense[l].weight), out=a_dy[l - 1][j], trans_w=True)
+                ops.gemm(dpre_in, W(lin_in.weight), out=dxin[j], trans_w=True)
                 have_carry = True
                 cur = 1 - cur
             if train:
-                param_grads(0, H)
+                actor_backward()
         return (None,) * (7 + ctx.n_params)
 
 

@@ -107,6 +107,61 @@ def test_ln_act(dtype, M, D, eps, act):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("frozen", [False, True])
+@pytest.mark.parametrize("M,D,eps,act,pad", [(20011, 1024, 1e-5, 1, 0), (10000, 1024, 1e-5, 0, 8), (250003, 48, 1e-3, 1, 0), (120001, 96, 1e-3, 1, 0),
+                                             (40000, 192, 1e-3, 1, 0), (30000, 384, 1e-3, 1, 16), (40000, 256, 1e-5, 1, 0)])
+def test_ln_act_large_rows_bulk_copy_pipeline(dtype, frozen, M, D, eps, act, pad):
+    """row counts above 4 tiles per SM run the cp.async.bulk pipelines of csrc/ln_pipe.cuh (forward; backward with and without the parameter
+    gradients); ragged last tiles, strided rows (pad > 0: per-row bulk copies) and every channel width of the conv stacks"""
+    with ops.use_dtype(dtype):
+        x = rnd(M, D).to(dtype)
+        g, b = 1 + 0.1 * rnd(D, seed=1), 0.1 * rnd(D, seed=2)
+        dy = rnd(M, D, seed=3).to(dtype)
+        xr = x.float().to(DEV).requires_grad_(True); gr = g.to(DEV).requires_grad_(True); br = b.to(DEV).requires_grad_(True)
+        y = F.layer_norm(xr, (D,), gr, br, eps)
+        y = F.silu(y) if act else y
+        y.backward(dy.float().to(DEV))
+        xbuf = torch.zeros(M, D + pad, device=DEV, dtype=dtype)
+        xbuf[:, :D] = x.to(DEV)
+        xd = xbuf[:, :D].detach().requires_grad_(True)
+        gd, bd = g.to(DEV), b.to(DEV)
+        if not frozen:
+            gd, bd = torch.nn.Parameter(gd), torch.nn.Parameter(bd)
+        yd = ops.ln_act(xd, gd, bd, eps, act)
+        dyb = torch.zeros(M, D + pad, device=DEV, dtype=dtype)
+        dyb[:, :D] = dy.to(DEV)
+        yd.backward(dyb[:, :D])
+        tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+        close(yd, y, msg="ln y", **tol)
+        close(xd.grad, xr.grad, msg="ln dx", **tol)
+        if not frozen:
+            # column sums over up to 250 000 rows: compare relative to the column's scale
+            scale = float(gr.grad.abs().max())
+            ptol = dict(rtol=1e-3, atol=1e-4 * scale) if dtype == torch.float32 else dict(rtol=3e-2, atol=2e-2 * scale)
+            close(gd.grad, gr.grad, msg="ln dgamma", **ptol)
+            close(bd.grad, br.grad, msg="ln dbeta", **ptol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M", [2400, 2960, 2961, 40000])
+def test_ln_act_bwd_frozen_row_variants(dtype, M):
+    """frozen-parameter row pass at D = 1024: the 4-warp / five-blocks-per-SM variant (2 368 < M <= 2 960 on 148 SMs: one wave for the
+    rollout's 2 400 rows) and the 8-warp variant give dx of the one-pass kernel with parameter gradients"""
+    D = 1024
+    with ops.use_dtype(dtype):
+        x = rnd(M, D).to(dtype)
+        g, b = 1 + 0.1 * rnd(D, seed=1), 0.1 * rnd(D, seed=2)
+        dy = rnd(M, D, seed=3).to(dtype)
+        xr = x.float().clone().requires_grad_(True)
+        F.silu(F.layer_norm(xr, (D,), g, b, 1e-5)).backward(dy.float())
+        xd = x.to(DEV).requires_grad_(True)
+        yd = ops.ln_act(xd, g.to(DEV), b.to(DEV), 1e-5, 1)          # gamma / beta without gradients -> ln_bwd_fast_kernel
+        yd.backward(dy.to(DEV))
+        tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+        close(xd.grad, xr.grad, msg="ln dx (frozen)", **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,K,N", [(130, 72, 64), (200, 264, 128), (333, 1034, 512), (2400, 2048, 1024)])
 def test_linear_ln_act_and_linear(dtype, M, K, N, monkeypatch):
     """N = 128..1024 in bf16 runs the cluster-fused GEMM + LayerNorm kernel (row statistics merged over DSMEM)"""
