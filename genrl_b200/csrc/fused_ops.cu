@@ -1076,7 +1076,7 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
         (!dhprev || vec_ok<float>(dhprev, lddhp)) && f32_vec_ok(gamma) && f32_vec_ok(beta)) {
       if (D == 1024)
         genrl::launch_pdl(gru_bwd_row1024_kernel<T>, (int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
-                                                                                               (T*)dz, lddz, dhprev, lddhp, M, (const T*)nullptr, 0LL, (const T*)nullptr, 0LL);
+                                                                                               (T*)dz, lddz, dhprev, lddhp, M, (const T*)nullptr, 0LL, (const T*)nullptr, 0LL, (const T*)nullptr, 0LL);
       else
         genrl::launch_pdl(gru_bwd_fast_kernel<T>, row_grid(M, 148 * 16), 256, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats, (T*)dz, lddz,
                                                                              dhprev, lddhp, M, D);
@@ -1089,19 +1089,20 @@ extern "C" int genrl_gru_bwd(void* stream, const float* dh, long long lddh, cons
   return check_launch("gru_bwd");
 }
 
-// frozen-weights GRU backward at D = 1024 whose incoming gradient is dh + e1 + e2 (e1 / e2 optional, activation dtype).  Returns 2 when the
+// frozen-weights GRU backward at D = 1024 whose incoming gradient is dh + e1 + e2 + e3 (e* optional, activation dtype).  Returns 2 when the
 // shape / alignment is not eligible (the caller then sums the contributions itself and calls genrl_gru_bwd).
 extern "C" int genrl_gru_bwd_sum(void* stream, const float* dh, long long lddh, const void* e1, long long lde1, const void* e2, long long lde2,
+                                 const void* e3, long long lde3,
                                  const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
                                  const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp, long long M, int D, int dtype) {
   if (M <= 0) return 0;
   if (D != 1024) return 2;
   DISPATCH_T(dtype, {
     if (!(vec_ok<T>(z, ldz) && vec_ok<T>(dz, lddz) && vec_ok<float>(hprev, ldh) && vec_ok<float>(dh, lddh) && (!dhprev || vec_ok<float>(dhprev, lddhp)) &&
-          (!e1 || vec_ok<T>(e1, lde1)) && (!e2 || vec_ok<T>(e2, lde2)) && f32_vec_ok(gamma) && f32_vec_ok(beta)))
+          (!e1 || vec_ok<T>(e1, lde1)) && (!e2 || vec_ok<T>(e2, lde2)) && (!e3 || vec_ok<T>(e3, lde3)) && f32_vec_ok(gamma) && f32_vec_ok(beta)))
       return 2;
     genrl::launch_pdl(gru_bwd_row1024_kernel<T>, (int)std::min<long long>(M, 148 * 16), 128, 0, ST(stream), dh, lddh, (const T*)z, ldz, gamma, beta, hprev, ldh, stats,
-                      (T*)dz, lddz, dhprev, lddhp, M, (const T*)e1, lde1, (const T*)e2, lde2);
+                      (T*)dz, lddz, dhprev, lddhp, M, (const T*)e1, lde1, (const T*)e2, lde2, (const T*)e3, lde3);
   });
   return check_launch("gru_bwd_sum");
 }

@@ -501,9 +501,10 @@ __global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ hprev, long long ldh, const float* __restrict__ stats,
                                                               T* __restrict__ dz, long long lddz, float* __restrict__ dhprev, long long lddhp, long long M,
-                                                              const T* __restrict__ e1, long long lde1, const T* __restrict__ e2, long long lde2) {
-  // e1 / e2 (optional, activation dtype): further contributions to d loss / d h summed on the fly (the rollout's feat-slice gradient and the
-  // h half of the previous step's GRU dgrad) instead of two accumulate-copy launches per step
+                                                              const T* __restrict__ e1, long long lde1, const T* __restrict__ e2, long long lde2,
+                                                              const T* __restrict__ e3, long long lde3) {
+  // e1 / e2 / e3 (optional, activation dtype): further contributions to d loss / d h summed on the fly (the rollout's feat-slice gradient, the
+  // h half of the previous step's GRU dgrad, the output block's dgrad) instead of accumulate-copy launches / fp32 accumulate epilogues
   genrl::pdl_sync();
   constexpr int D = 1024, D3 = 3072;
   __shared__ float red[2][4];
@@ -520,6 +521,9 @@ __global__ void __launch_bounds__(128) gru_bwd_row1024_kernel(const float* __res
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] += t[k]; }
     if (e2) { float t[8]; V8<T>::load(e2 + row * lde2 + j, t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += t[k]; }
+    if (e3) { float t[8]; V8<T>::load(e3 + row * lde3 + j, t);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] += t[k]; }
     gru_gate8<(sizeof(T) == 2)>(a, b, c, mean, rstd, gamma, beta, D, j, r, cand, u, pc, xr, xc, xu);

@@ -44,6 +44,20 @@ def supported(policy, rssm):
     return True
 
 
+class _Win:
+    """column window [c0, c1) of a [steps, N, ld] buffer: per-step views and the rows of several steps as one strided matrix"""
+
+    def __init__(self, t, c0, c1):
+        self.t, self.c0, self.c1 = t, c0, c1
+
+    def __getitem__(self, i):
+        return self.t[i][:, self.c0:self.c1]
+
+    def all(self, lo=0, hi=None):
+        hi = self.t.shape[0] if hi is None else hi
+        return self.t[lo:hi].reshape(-1, self.t.shape[2])[:, self.c0:self.c1]
+
+
 class _Slab:
     """[steps, N, cols] buffer in a given dtype whose rows keep a TMA-legal leading dimension"""
 
@@ -104,7 +118,19 @@ class _Rollout(Function):
         lin_dist = rssm._ensemble_img_dist[0]
         w_gru, ln_gru = rssm._cell._layer.weight, rssm._cell._norm
         # ---- buffers -----------------------------------------------------------------------------------------------------------------------
-        feat = _Slab(H + 1, N, SK + D, cd, dev)
+        # ONE row per (step, sample) holds every operand the next step's GEMMs read, so no copy kernel runs between the steps:
+        #   [ action_{i+1} (padded to a0) | stoch_i (SK) | deter_i (D) | x_{i+1} (Hd) ]
+        #   img_in input  [action | stoch] = cols [0, a0+SK)        (W_in with its columns permuted to [action | 0 | stoch])
+        #   actor input   feat_i           = cols [a0, a0+SK+D)
+        #   GRU input     [deter | x]      = cols [a0+SK, a0+SK+D+Hd)   (W_gru with its columns permuted to [h | x])
+        a0 = _pad8(A)
+        o_s, o_d, o_x, o_e = a0, a0 + SK, a0 + SK + D, a0 + SK + D + Hd
+        slab = torch.empty(H + 1, N, o_e, device=dev, dtype=cd)
+        slab[:, :, :a0].zero_()                                   # padded action columns meet zero weights: they must be finite
+        feat = _Win(slab, o_s, o_x)
+        w_in_c, w_gru_c = W(lin_in.weight), W(w_gru)
+        w_in_p = torch.cat([w_in_c[:, SK:SK + A], w_in_c.new_zeros(Hd, a0 - A), w_in_c[:, :SK]], 1)       # [Hd, a0 + SK]
+        w_gru_p = torch.cat([w_gru_c[:, Hd:Hd + D], w_gru_c[:, :Hd]], 1)                                   # [3D, D + Hd]
         stoch = torch.empty(H + 1, N, SK, device=dev, dtype=torch.float32)
         deter = torch.empty(H + 1, N, D, device=dev, dtype=torch.float32)
         logit = torch.empty(H + 1, N, SK, device=dev, dtype=torch.float32)
@@ -118,25 +144,24 @@ class _Rollout(Function):
         in_pre, in_st = _Slab(H, N, Hd, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
         z, g_st = _Slab(H, N, 3 * D, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
         out_pre, out_st = _Slab(H, N, Hd, cd, dev), torch.empty(H, N, 2, device=dev, dtype=torch.float32)
-        xin = _Slab(1, N, SK + A, cd, dev, zero=True)[0]             # [stoch_{i-1} | action_i]
-        xh = _Slab(1, N, Hd + D, cd, dev)[0]                        # [x | deter_{i-1}]
         y_out = _Slab(1, N, Hd, cd, dev)[0]
         # ---- step 0 = the start state ------------------------------------------------------------------------------------------------------
         stoch[0].copy_(stoch0.reshape(N, SK))
         deter[0].copy_(deter0)
         logit[0].copy_(logit0.reshape(N, SK))
-        _copy(stoch[0], feat[0][:, :SK]); _copy(deter[0], feat[0][:, SK:])
-        _copy(stoch[0], xin[:, :SK]); _copy(deter[0], xh[:, Hd:])
+        _copy(stoch[0], slab[0][:, o_s:o_d]); _copy(deter[0], slab[0][:, o_d:o_x])
         if not isinstance(noise, ops.PhiloxNoise):       # dreamer.py:259-260 samples (and discards) one action at the start state: keep the
             noise.randn_into(torch.empty(N, A, device=dev, dtype=torch.float32))      # replayed reference draws in step
         step_ptr = ops.noise_step_ptr(dev)
         big = N >= ops.CHAIN_MIN_ROWS
-        chain_a = big and ops.chain_supported(U, cd) and all(n.eps == norms[0].eps for n in norms) and (SK + D) % 8 == 0
-        chain_h = big and ops.chain_supported(Hd, cd) and (SK + D) % 8 == 0 and SK % 8 == 0
+        aligned = o_e % 8 == 0 and SK % 8 == 0 and D % 8 == 0
+        chain_a = big and ops.chain_supported(U, cd) and all(n.eps == norms[0].eps for n in norms) and aligned
+        chain_h = big and ops.chain_supported(Hd, cd) and aligned
         for i in range(1, H + 1):
             j = i - 1
+            rj, ri = slab[j], slab[i]
             # actor on sg(feat_{i-1})                                                                     dreamer.py:265-266, dreamer_utils.py:738-747
-            x = feat[j]
+            x = rj[:, o_s:o_x]
             if chain_a:
                 # the whole trunk in one persistent cluster launch (csrc/mlp_chain.cu)
                 ops.mlp_chain_fwd(x, [W(d.weight) for d in dense], [d.bias.detach() if d.bias is not None else None for d in dense],
@@ -152,33 +177,32 @@ class _Rollout(Function):
             e = None
             if not eval_policy:
                 e = noise.randn_into(eps[j])
-            lib.genrl_actor_head_fwd(_st(), _p(out2[j]), 2 * A, _p(e), int(bool(eval_policy)), _p(action[i]), A, _p(xin[:, SK:]), _ld(xin), _p(ent[j]),
+            lib.genrl_actor_head_fwd(_st(), _p(out2[j]), 2 * A, _p(e), int(bool(eval_policy)), _p(action[i]), A, _p(rj[:, :A]), _ld(rj), _p(ent[j]),
                                      N, A, _CODE[cd])
             # img_step                                                                                     dreamer_utils.py:459-487
+            xin, xdst = rj[:, :o_d], rj[:, o_x:o_e]
             if chain_h:
-                ops.mlp_chain_fwd(xin, [W(lin_in.weight)], [lin_in.bias.detach()], [ln_in.weight], [ln_in.bias], ln_in.eps, ACT_SILU,
-                                  [in_pre[j]], [xh[:, :Hd]], [in_st[j]])
+                ops.mlp_chain_fwd(xin, [w_in_p], [lin_in.bias.detach()], [ln_in.weight], [ln_in.bias], ln_in.eps, ACT_SILU,
+                                  [in_pre[j]], [xdst], [in_st[j]])
             else:
-                ops.gemm(xin, W(lin_in.weight), out=in_pre[j], bias=lin_in.bias.detach())
-                _ln_fwd(in_pre[j], ln_in.weight, ln_in.bias, ln_in.eps, xh[:, :Hd], in_st[j])
-            ops.gemm(xh, W(w_gru), out=z[j])
+                ops.gemm(xin, w_in_p, out=in_pre[j], bias=lin_in.bias.detach())
+                _ln_fwd(in_pre[j], ln_in.weight, ln_in.bias, ln_in.eps, xdst, in_st[j])
+            ops.gemm(rj[:, o_d:o_e], w_gru_p, out=z[j])
             lib.genrl_gru_fwd(_st(), _p(z[j]), _ld(z[j]), _p(ln_gru.weight), _p(ln_gru.bias), _p(deter[j]), D, _p(deter[i]), D,
-                              _p(feat[i][:, SK:]), _ld(feat[i]), _p(g_st[j]), N, D, _CODE[cd])
+                              _p(ri[:, o_d:o_x]), _ld(ri), _p(g_st[j]), N, D, _CODE[cd])
             if chain_h:
-                ops.mlp_chain_fwd(feat[i][:, SK:], [W(lin_out.weight)], [lin_out.bias.detach()], [ln_out.weight], [ln_out.bias], ln_out.eps, ACT_SILU,
+                ops.mlp_chain_fwd(ri[:, o_d:o_x], [W(lin_out.weight)], [lin_out.bias.detach()], [ln_out.weight], [ln_out.bias], ln_out.eps, ACT_SILU,
                                   [out_pre[j]], [y_out], [out_st[j]])
             else:
-                ops.gemm(feat[i][:, SK:], W(lin_out.weight), out=out_pre[j], bias=lin_out.bias.detach())
+                ops.gemm(ri[:, o_d:o_x], W(lin_out.weight), out=out_pre[j], bias=lin_out.bias.detach())
                 _ln_fwd(out_pre[j], ln_out.weight, ln_out.bias, ln_out.eps, y_out, out_st[j])
             ops.gemm(y_out, W(lin_dist.weight), out=logit[i], bias=lin_dist.bias.detach())
             noise.randint()
             nz, seed, off = noise.exp(N * S, K, dev)
-            lib.genrl_cat_sample_fwd(_st(), _p(logit[i]), _p(nz), seed, off, step_ptr if nz is None else None, 1, _p(feat[i][:, :SK]), _ld(feat[i]),
+            lib.genrl_cat_sample_fwd(_st(), _p(logit[i]), _p(nz), seed, off, step_ptr if nz is None else None, 1, _p(ri[:, o_s:o_d]), _ld(ri),
                                      _p(stoch[i]), SK, None, N, S, K, _CODE[cd])
-            if i < H:
-                _copy(feat[i][:, :SK], xin[:, :SK]); _copy(feat[i][:, SK:], xh[:, Hd:])
-        feat_out = feat.t[:, :, :SK + D]
-        ctx.mods = (policy, rssm, dense, norms, w_head)
+        feat_out = slab[:, :, o_s:o_x]
+        ctx.mods = (policy, rssm, dense, norms, w_head, w_in_p, w_gru_p, a0)
         ctx.dims = (S, K, D, Hd, N, H, L, U, A, cd, bool(eval_policy))
         ctx.bufs = dict(feat=feat, deter=deter, logit=logit, a_pre=a_pre, a_y=a_y, a_st=a_st, out2=out2, eps=eps, in_pre=in_pre, in_st=in_st, z=z,
                         g_st=g_st, out_pre=out_pre, out_st=out_st)
@@ -189,7 +213,7 @@ class _Rollout(Function):
 
     @staticmethod
     def backward(ctx, dfeat, dstoch, _ddeter, _dlogit, _daction, dent):
-        policy, rssm, dense, norms, w_head = ctx.mods
+        policy, rssm, dense, norms, w_head, w_in_p, w_gru_p, a0 = ctx.mods
         S, K, D, Hd, N, H, L, U, A, cd, eval_policy = ctx.dims
         b = ctx.bufs
         SK = S * K
@@ -199,7 +223,7 @@ class _Rollout(Function):
             lin_in, ln_in = rssm._img_in[0], rssm._img_in[1]._layer
             lin_out, ln_out = rssm._ensemble_img_out[0][0], rssm._ensemble_img_out[0][1]._layer
             lin_dist = rssm._ensemble_img_dist[0]
-            w_gru_c, ln_gru = W(rssm._cell._layer.weight), rssm._cell._norm
+            ln_gru = rssm._cell._norm
             if dfeat is not None:
                 dfeat = dfeat if (dfeat.dtype == cd and dfeat.stride(-1) == 1) else dfeat.to(cd).contiguous()
             if dstoch is not None:
@@ -215,14 +239,15 @@ class _Rollout(Function):
             dpre_out = _Slab(1, N, Hd, cd, dev)[0]
             dz = _Slab(1, N, 3 * D, cd, dev)[0]
             dx = _Slab(1, N, Hd, cd, dev)[0]
-            dxh = [_Slab(1, N, Hd + D, cd, dev)[0], _Slab(1, N, Hd + D, cd, dev)[0]]
+            dxh = [_Slab(1, N, D + Hd, cd, dev)[0], _Slab(1, N, D + Hd, cd, dev)[0]]      # [d deter_{i-1} | d x_i] (the permuted weight's order)
             fold_ok = D == 1024 and cd == torch.bfloat16
             pending_h = None
+            dgo = _Slab(1, N, D, cd, dev)[0]                               # d deter_i through the prior's output block
             merged_gru_dgrad = cd == torch.bfloat16 and N >= 1024
             dpre_in = _Slab(1, N, Hd, cd, dev)[0]
             # d loss / d [stoch_{i-1} | action_i] of EVERY step: the stoch part is the next iteration's carry, the action part is all the actor's
             # backward needs, so the actor's whole backward runs ONCE over the H*N rows after the loop (below)
-            dxin = _Slab(H, N, SK + A, cd, dev)
+            dxin = _Slab(H, N, a0 + SK, cd, dev)                       # [d action_i (a0) | d stoch_{i-1}]
             train = H > 0 and dense[0].weight.requires_grad
 
             def actor_backward():
@@ -235,7 +260,7 @@ class _Rollout(Function):
                 e = None if eval_policy else b["eps"].reshape(M, A)
                 if e is None:
                     e = torch.zeros(M, A, device=dev, dtype=torch.float32)
-                DA = dxin.all()[:, SK:]
+                DA = dxin.all()[:, :A]
                 DO = dout2c.all()
                 lib.genrl_actor_head_bwd(st, _p(b["out2"]), 2 * A, _p(e), _p(DA), _ld(DA), _p(dent), 1.0 if dent is not None else 0.0,
                                          _p(DO), _ld(DO), _CODE[cd], M, A, _CODE[cd])
@@ -273,7 +298,7 @@ class _Rollout(Function):
                 if dstoch is not None:
                     srcs.append(dstoch[i])
                 if have_carry:
-                    srcs.append(dxin[i][:, :SK])
+                    srcs.append(dxin[i][:, a0:])
                 gh = G[cur]
                 # further contributions to d loss / d deter_i, summed inside the GRU backward kernel when it can (else by accumulate-copies)
                 extras = []
@@ -300,13 +325,18 @@ class _Rollout(Function):
                             _copy(dlogit, dlogit_c)
                     ops.gemm(dlogit_c, W(lin_dist.weight), out=dy_out, trans_w=True)
                     _ln_bwd(dy_out, b["out_pre"][j], ln_out.weight, ln_out.bias, b["out_st"][j], dpre_out)
-                    ops.gemm(dpre_out, W(lin_out.weight), out=gh, trans_w=True, accumulate=True)
+                    if fold:
+                        # activation-dtype output (the plain epilogue), summed inside the GRU backward kernel below
+                        ops.gemm(dpre_out, W(lin_out.weight), out=dgo, trans_w=True)
+                        extras.append(dgo)
+                    else:
+                        ops.gemm(dpre_out, W(lin_out.weight), out=gh, trans_w=True, accumulate=True)
                 # ---- GRU cell -------------------------------------------------------------------------------------------------------------
                 gn = G[1 - cur]
                 if extras:
-                    e1 = extras[0]
-                    e2 = extras[1] if len(extras) > 1 else None
-                    lib.genrl_gru_bwd_sum(_st(), _p(gh), D, _p(e1), _ld(e1), _p(e2), _ld(e2) if e2 is not None else 0, _p(b["z"][j]), _ld(b["z"][j]),
+                    ex = extras + [None] * (3 - len(extras))
+                    lib.genrl_gru_bwd_sum(_st(), _p(gh), D, _p(ex[0]), _ld(ex[0]), _p(ex[1]), _ld(ex[1]) if ex[1] is not None else 0,
+                                          _p(ex[2]), _ld(ex[2]) if ex[2] is not None else 0, _p(b["z"][j]), _ld(b["z"][j]),
                                           _p(ln_gru.weight), _p(ln_gru.bias), _p(b["deter"][j]), D, _p(b["g_st"][j]), _p(dz), _ld(dz), _p(gn), D,
                                           N, D, _CODE[cd])
                 else:
@@ -315,16 +345,16 @@ class _Rollout(Function):
                 if i > 1 and merged_gru_dgrad:
                     # one dgrad GEMM for [x | h] (N = Hd + D: enough 256x256 tiles for the 2-CTA kernel); the h half joins the carry inside the
                     # next iteration's GRU backward (or by an accumulate-copy when that kernel is not eligible)
-                    ops.gemm(dz, w_gru_c, out=dxh[i & 1], trans_w=True)
-                    pending_h = dxh[i & 1][:, Hd:]
-                    dx_i = dxh[i & 1][:, :Hd]
+                    ops.gemm(dz, w_gru_p, out=dxh[i & 1], trans_w=True)
+                    pending_h = dxh[i & 1][:, :D]
+                    dx_i = dxh[i & 1][:, D:]
                 else:
-                    ops.gemm(dz, w_gru_c[:, :Hd], out=dx, trans_w=True)
+                    ops.gemm(dz, w_gru_p[:, D:], out=dx, trans_w=True)
                     if i > 1:
-                        ops.gemm(dz, w_gru_c[:, Hd:], out=gn, trans_w=True, accumulate=True)
+                        ops.gemm(dz, w_gru_p[:, :D], out=gn, trans_w=True, accumulate=True)
                     dx_i = dx
                 _ln_bwd(dx_i, b["in_pre"][j], ln_in.weight, ln_in.bias, b["in_st"][j], dpre_in)
-                ops.gemm(dpre_in, W(lin_in.weight), out=dxin[j], trans_w=True)
+                ops.gemm(dpre_in, w_in_p, out=dxin[j], trans_w=True)
                 have_carry = True
                 cur = 1 - cur
             if train:

@@ -68,10 +68,11 @@ int genrl_gru_fwd(void* stream, const void* z, long long ldz, const float* gamma
 int genrl_gru_bwd(void* stream, const float* dh, long long lddh, const void* z, long long ldz, const float* gamma, const float* beta,
                   const float* hprev, long long ldh, const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp,
                   float* dgamma, float* dbeta, long long M, int D, int dtype);
-/* Frozen-weights GRU backward (D = 1024) whose incoming gradient is dh + e1 + e2: e1 / e2 (optional, activation dtype) are the other
- * contributions to d loss / d deter_i inside the imagination rollout's reverse loop (agent/dreamer.py:254-287): the feat-slice gradient and the
- * h half of the previous step's GRU dgrad.  Returns 2 when the shape / alignment is not eligible. */
+/* Frozen-weights GRU backward (D = 1024) whose incoming gradient is dh + e1 + e2 + e3: e1 / e2 / e3 (optional, activation dtype) are the other
+ * contributions to d loss / d deter_i inside the imagination rollout's reverse loop (agent/dreamer.py:254-287): the feat-slice gradient, the
+ * h half of the previous step's GRU dgrad and the dgrad of the prior's output block.  Returns 2 when the shape / alignment is not eligible. */
 int genrl_gru_bwd_sum(void* stream, const float* dh, long long lddh, const void* e1, long long lde1, const void* e2, long long lde2,
+                      const void* e3, long long lde3,
                       const void* z, long long ldz, const float* gamma, const float* beta, const float* hprev, long long ldh,
                       const float* stats, void* dz, long long lddz, float* dhprev, long long lddhp, long long M, int D, int dtype);
 
