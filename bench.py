@@ -548,6 +548,22 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
                             "gbs_vs_streamed": streamed / (obs_us * 1e-6) / 1e9, "frac_vs_streamed": streamed / (obs_us * 1e-6) / 1e9 / pk["hbm"],
                             "note": "SURVEY §8d: 'streamed' is the figure when the recurrent weights exceed the 33 MB of aggregate shared memory "
                                     "(fp32: 37.8 MB) and are re-read every time step; this design keeps the W_h slice resident instead"}}
+    ss_l, ss_us = fam("rssm_scan_stream_fwd_kernel")
+    if ss_us > 0:
+        # weight-streaming regime (preset c5, deter = 4096): per time step the kernel streams 3 D^2 bf16 weight bytes; per launch also gx in
+        # (fp32), deter out (fp32), m*h_prev out and the pre-activations z out (bf16)
+        B, T = args.batch, args.length
+        D = int(agent.wm.rssm._deter)
+        N = B * T
+        wbytes = 3 * D * D * 2
+        kbytes = T * wbytes + N * (3 * D * 4 + D * 4 + D * 2 + 3 * D * 2 + 8)
+        us = ss_us / ss_l
+        out["roofline_rssm"] = {
+            "kernel": "rssm_scan_stream_fwd_kernel (persistent, W_h streamed once per time step into mma.sync A fragments)", "bound": "hbm", "unit": "GB/s",
+            "peak": pk["hbm"], "peak_source": pk["source"] + " HBM copy", "launches_per_step": ss_l / n, "us_per_launch": us, "us_per_time_step": us / T,
+            "weight_bytes_per_time_step": wbytes, "kernel_bytes_per_launch": kbytes, "achieved": kbytes / (us * 1e-6) / 1e9,
+            "frac": kbytes / (us * 1e-6) / 1e9 / pk["hbm"],
+            "note": "up to 75 MB of the weights are kept in L2 between time steps (evict_last), so part of the streamed bytes is served by L2, not HBM"}
     return out
 
 

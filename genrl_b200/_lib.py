@@ -46,7 +46,7 @@ class GenrlError(RuntimeError):
     pass
 
 
-_NO_LAUNCH = ("genrl_abi_version", "genrl_pack_entry_size", "genrl_device_info")
+_NO_LAUNCH = ("genrl_abi_version", "genrl_pack_entry_size", "genrl_device_info", "genrl_rssm_scan_stream_supported")
 
 
 class _Lib:

@@ -1231,9 +1231,85 @@ def _gru_scan_stepwise(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
     return torch.stack(outs, 1).reshape(B * T, D)
 
 
+class _GruScanStream(Function):
+    """The same recurrence for hidden sizes whose W_h cannot stay resident in shared memory (BASELINE configs[4], D = 4096): the forward is ONE
+    persistent cooperative kernel that streams the bf16 weights once per time step (csrc/rssm_scan_stream.cu); the backward walks the steps with
+    the GRU-gate backward kernel and one M = B dgrad GEMM per step, the W_h gradient is one GEMM over all B*T rows afterwards."""
+
+    @staticmethod
+    def forward(ctx, gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
+        gx = gx.contiguous().float()
+        D = gx.shape[1] // 3
+        dev = gx.device
+        wc = compute_weight(w_gru)                       # bf16 shadow [3D, Hd + D]
+        wh = wc[:, Hd:Hd + D]
+        deter = torch.empty(B * T, D, device=dev, dtype=torch.float32)
+        hprev = torch.empty(B * T, D, device=dev, dtype=torch.bfloat16)
+        z = torch.empty(B * T, 3 * D, device=dev, dtype=torch.bfloat16)
+        stats = torch.empty(B * T, 2, device=dev, dtype=torch.float32)
+        h0c = None if h0 is None else h0.contiguous().float()
+        maskc = None if mask is None else mask.contiguous().float()
+        ws = _scan_workspace(B, T, D, dev)
+        lib.genrl_rssm_scan_stream_fwd(_st(), B, T, D, _p(gx), _p(wh), _ld(wh), _p(gamma), _p(beta), _p(maskc), _p(h0c), _p(deter), _p(hprev), D,
+                                       _p(z), 3 * D, _p(stats), _p(ws))
+        ctx.save_for_backward(z, stats, deter, hprev, maskc, h0c)
+        ctx.w, ctx.gamma, ctx.beta, ctx.cfg = w_gru, gamma, beta, (B, T, D, Hd)
+        return deter
+
+    @staticmethod
+    def backward(ctx, ddeter):
+        z, stats, deter, hprev, mask, h0c = ctx.saved_tensors
+        B, T, D, Hd = ctx.cfg
+        w, dev = ctx.w, z.device
+        with use_dtype(torch.bfloat16):
+            wh = compute_weight(w)[:, Hd:Hd + D]
+            dd3 = ddeter.contiguous().float().view(B, T, D)
+            det3, z3, st3 = deter.view(B, T, D), z.view(B, T, 3 * D), stats.view(B, T, 2)
+            m3 = None if mask is None else mask.view(B, T, 1)
+            dz = torch.empty(B * T, 3 * D, device=dev, dtype=torch.bfloat16)
+            dz3 = dz.view(B, T, 3 * D)
+            train = w.requires_grad
+            gb = bb = dg = db = None
+            if train:
+                gb, dg = _grad_buf(ctx.gamma)
+                bb, db = _grad_buf(ctx.beta)
+            carry = None
+            for t in range(T - 1, -1, -1):
+                dh = dd3[:, t].contiguous() if carry is None else dd3[:, t] + carry
+                hp = det3[:, t - 1] if t > 0 else (h0c if h0c is not None else torch.zeros(B, D, device=dev, dtype=torch.float32))
+                if m3 is not None:
+                    hp = hp * m3[:, t]
+                hp = hp.contiguous()
+                st_t = st3[:, t].contiguous()
+                zt, dzt = z3[:, t], dz3[:, t]
+                dhp = torch.empty(B, D, device=dev, dtype=torch.float32)
+                lib.genrl_gru_bwd(_st(), _p(dh), D, _p(zt), _ld(zt), _p(ctx.gamma), _p(ctx.beta), _p(hp), D, _p(st_t), _p(dzt), _ld(dzt), _p(dhp), D,
+                                  _p(gb), _p(bb), B, D, _CODE[torch.bfloat16])
+                # d(m_t h_{t-1}) = (1 - u) dh + dz_t W_h;  times the reset mask = the gradient reaching h_{t-1}
+                gemm(dzt, wh, out=dhp, trans_w=True, accumulate=True)
+                carry = dhp if m3 is None else dhp * m3[:, t]
+            dh0 = carry if (h0c is not None and ctx.needs_input_grad[5]) else None
+            dw = None
+            if train:
+                gbuf, dw_ret = _grad_buf(w)
+                gemm(dz, hprev, out=gbuf[:, Hd:], trans_a=True, trans_w=True, accumulate=True)
+                dw = dw_ret
+        ctx.dz_compute = dz
+        return cast_to(dz, torch.float32), dw, dg, db, None, dh0, None, None, None
+
+
+def scan_stream_supported(B, D):
+    """the weight-streaming scan: bf16 mode, at most 16 sequences per GPU, D a multiple of 128 with D/32 CTAs co-resident"""
+    import os
+    return (_State.dtype == torch.bfloat16 and os.environ.get("GENRL_SCAN_STREAM", "1") != "0"
+            and bool(lib.load().genrl_rssm_scan_stream_supported(int(B), int(D))))
+
+
 def gru_scan(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
     """gx fp32 [B*T, 3D] (x-part pre-activations incl. nothing else), returns deter fp32 [B*T, D] (row n = b*T + t)."""
     if not scan_supported(gx.shape[1] // 3):
+        if scan_stream_supported(B, gx.shape[1] // 3):
+            return _GruScanStream.apply(gx, w_gru, gamma, beta, mask, h0, B, T, Hd)
         return _gru_scan_stepwise(gx, w_gru, gamma, beta, mask, h0, B, T, Hd)
     return _GruScan.apply(gx, w_gru, gamma, beta, mask, h0, B, T, Hd)
 

@@ -193,6 +193,15 @@ int genrl_rssm_scan_bwd(void* stream, int B, int T, int D, const float* dh_ext, 
                         long long ldw, const float* gamma, const float* beta, const float* mask, const float* deter, const float* h0,
                         void* dz_t, long long ld_dz, int t_dtype, float* dh0, float* dgamma, float* dbeta, void* workspace);
 
+/* Weight-streaming variant of the same time loop for hidden sizes whose recurrent matrix cannot stay resident in shared memory
+ * (BASELINE configs[4]: deter = 4096): W_h (bf16 [3D, D], row stride ldw) is streamed from L2 / HBM once per time step straight into
+ * mma.sync A fragments, the <= 16 batch rows are the N operand.  Forward only (the backward of this shape runs step by step on
+ * genrl_gru_bwd + genrl_gemm).  hprev / z: bf16 outputs [B*T, D] / [B*T, 3D]; workspace as for genrl_rssm_scan_fwd. */
+int genrl_rssm_scan_stream_supported(int B, int D);      /* 1 / 0, no launch */
+int genrl_rssm_scan_stream_fwd(void* stream, int B, int T, int D, const float* gx, const void* Wh, long long ldw, const float* gamma,
+                               const float* beta, const float* mask, const float* h0, float* deter, void* hprev, long long ld_hp,
+                               void* z, long long ld_z, float* stats, void* workspace);
+
 #ifdef __cplusplus
 }
 #endif

@@ -512,6 +512,56 @@ def test_gru_scan_matches_stepwise(dtype, B, T, D, Hd, resets):
         close(wd.grad[:, Hd:], wr.grad[:, Hd:], msg="scan dW_h", **tol)
 
 
+@pytest.mark.parametrize("B,T,D,Hd,resets", [(16, 4, 2048, 512, True), (7, 3, 4096, 256, True), (1, 5, 1280, 128, False)])
+def test_gru_scan_weight_streaming_matches_stepwise(B, T, D, Hd, resets, monkeypatch):
+    """hidden sizes above 8 x #SMs (BASELINE configs[4]: D = 4096) run the weight-streaming scan (csrc/rssm_scan_stream.cu): forward values
+    and every gradient against T sequential fp32 GRU steps; the op-level path it replaces gives the same numbers"""
+    with ops.use_dtype(torch.bfloat16):
+        assert not ops.scan_supported(D) and ops.scan_stream_supported(B, D)
+        torch.manual_seed(1)
+        w = torch.randn(3 * D, Hd + D) / math.sqrt(Hd + D)
+        g, b = 1 + 0.1 * rnd(3 * D, seed=2), 0.1 * rnd(3 * D, seed=3)
+        gx = rnd(B * T, 3 * D, seed=4)
+        h0 = rnd(B, D, seed=5) * 0.5
+        mask = torch.ones(B, T)
+        if resets:
+            mask[:, 0] = 0; mask[0, T // 2] = 0
+        dd = rnd(B * T, D, seed=6)
+        wq = w.to(torch.bfloat16).float()
+        wr = wq.to(DEV).requires_grad_(True); gr = g.to(DEV).requires_grad_(True); br = b.to(DEV).requires_grad_(True)
+        gxr = gx.to(DEV).requires_grad_(True); h0r = h0.to(DEV).requires_grad_(True)
+        md = mask.to(DEV)
+        h = h0r
+        outs = []
+        gx3 = gxr.reshape(B, T, 3 * D)
+        for t in range(T):
+            hm = h * md[:, t:t + 1]
+            z = gx3[:, t] + hm @ wr[:, Hd:].t()
+            parts = F.layer_norm(z, (3 * D,), gr, br, 1e-5)
+            r, c, u = torch.chunk(parts, 3, -1)
+            r = torch.sigmoid(r); c = torch.tanh(r * c); u = torch.sigmoid(u - 1)
+            h = u * c + (1 - u) * hm
+            outs.append(h)
+        deter = torch.stack(outs, 1).reshape(B * T, D)
+        (deter * dd.to(DEV)).sum().backward()
+
+        def run():
+            wd = torch.nn.Parameter(w.to(DEV)); gd = torch.nn.Parameter(g.to(DEV)); bd = torch.nn.Parameter(b.to(DEV))
+            gxd = gx.to(DEV).requires_grad_(True); h0d = h0.to(DEV).requires_grad_(True)
+            dt = ops.gru_scan(gxd, wd, gd, bd, md.reshape(-1).contiguous(), h0d, B, T, Hd)
+            (dt * dd.to(DEV)).sum().backward()
+            return dt, gxd.grad, h0d.grad, gd.grad, bd.grad, wd.grad[:, Hd:]
+
+        got = run()
+        ref = (deter, gxr.grad, h0r.grad, gr.grad, br.grad, wr.grad[:, Hd:])
+        tols = [dict(rtol=1e-2, atol=1e-2)] + [dict(rtol=3e-2, atol=3e-2)] * 5
+        for name, a, e, tol in zip(("deter", "dgx", "dh0", "dgamma", "dbeta", "dW_h"), got, ref, tols):
+            close(a, e, msg="stream scan " + name, **tol)
+        monkeypatch.setenv("GENRL_SCAN_STREAM", "0")
+        old = run()
+        close(got[0], old[0], msg="stream vs op-level deter", rtol=1e-2, atol=1e-2)
+
+
 @pytest.mark.parametrize("dtype,T,N,E,align", [(torch.float32, 11, 37, 96, True), (torch.float32, 16, 64, 1536, True),
                                                (torch.bfloat16, 16, 50, 1536, True), (torch.float32, 5, 9, 64, False)])
 def test_vlm_reward_alignment_and_gradient(dtype, T, N, E, align):
