@@ -143,12 +143,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = m0 + quarter * 32 + lane;
     const bool row_ok = row < p.M;
     const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+    // Coalesced stores: an epilogue thread owns one ROW of the accumulator, so a direct 16-byte store per lane touches 32 different 128-byte
+    // lines per instruction (one L1 tag cycle each).  The main loop is over (every pipeline stage has been consumed), so each warp transposes
+    // its 32 rows x 32 columns chunk through a private piece of the pipeline's shared memory and writes 4 rows x 128 bytes (fp32) or
+    // 8 rows x 64 bytes (bf16) per instruction.  Ragged column tiles, unaligned outputs and the split-K atomics keep the per-lane path.
+    uint8_t* stg = smem + (warp - 2) * (32 * 144);
+    const size_t esz = p.c_dtype == GENRL_F32 ? 4 : 2;
+    const bool ld_ok = ((size_t)p.ldc * esz) % 16 == 0 && !p.atomic;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       if (n0 + c >= p.N) break;                  // warp-uniform
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
-      if (!row_ok) continue;
       const int col0 = n0 + c;
       const int ncols = min(32, p.N - col0);
       float f[32];
@@ -158,47 +164,65 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(p.bias + col0 + j);
       }
+      const bool staged = ld_ok && ncols == 32 && ((reinterpret_cast<uintptr_t>(p.C) + (size_t)col0 * esz) & 15) == 0;      // warp-uniform
+      if (staged && p.c_dtype == GENRL_F32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * 144 + j * 4) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), piece = lane & 7;
+          float4 o = *reinterpret_cast<const float4*>(stg + rr * 144 + piece * 16);
+          const int grow = m0 + quarter * 32 + rr;
+          if (grow < p.M) {
+            float* out = reinterpret_cast<float*>(p.C) + (size_t)grow * p.ldc + col0 + piece * 4;
+            if (p.accumulate) {
+              const float4 prev = *reinterpret_cast<const float4*>(out);
+              o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+            }
+            *reinterpret_cast<float4*>(out) = o;
+          }
+        }
+        __syncwarp();
+        continue;
+      }
+      if (staged) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+          pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+          *reinterpret_cast<uint4*>(stg + lane * 80 + j * 2) = pk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = i * 8 + (lane >> 2), piece = lane & 3;
+          const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * 80 + piece * 16);
+          const int grow = m0 + quarter * 32 + rr;
+          if (grow < p.M) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)grow * p.ldc + col0 + piece * 8) = w;
+        }
+        __syncwarp();
+        continue;
+      }
+      if (!row_ok) continue;
       if (p.c_dtype == GENRL_F32) {
         float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
         if (p.atomic) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(out + j, f[j]);
         } else {
-          const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-          if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if (p.accumulate) {
-                float4 prev = *reinterpret_cast<float4*>(out + j);
-                o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
-              }
-              *reinterpret_cast<float4*>(out + j) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = p.accumulate ? out[j] + f[j] : f[j];
-          }
+          for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = p.accumulate ? out[j] + f[j] : f[j];
         }
       } else {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0;
-        const bool vec = ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162 a0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-            __nv_bfloat162 a1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-            __nv_bfloat162 a2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-            __nv_bfloat162 a3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
-            pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
-            *reinterpret_cast<uint4*>(out + j) = pk;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
-        }
+        for (int j = 0; j < 32; ++j) if (j < ncols) out[j] = __float2bfloat16_rn(f[j]);
       }
     }
   }

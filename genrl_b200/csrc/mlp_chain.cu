@@ -30,7 +30,13 @@ constexpr int CH_MAXL = 6;
 constexpr int CH_A_BYTES = CH_BM * CH_BK * 2;      // 16 KB
 constexpr int CH_B_BYTES = CH_BN * CH_BK * 2;      // 32 KB
 constexpr int CH_STAGE_BYTES = CH_A_BYTES + CH_B_BYTES;
-constexpr int CH_SMEM = CH_STAGES * CH_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 8 /*row partials*/ + 3 * CH_BN * 4 /*column params*/;
+// epilogue staging: an epilogue thread owns one ROW of the accumulator, so a direct 16-byte store per lane touches 32 different 128-byte lines
+// per instruction (one L1 tag cycle each: 8 warps x 32 stores x 32 lines = 8 192 cycles = 4 us per layer).  Each warp therefore transposes its
+// 32 rows x 32 columns chunk through a private 32 x 80-byte buffer and writes 8 rows x 64 bytes per instruction (8 lines).
+constexpr int CH_STG_ROW = 80;                     // 64 data bytes + 16 padding (conflict-free 16-byte accesses in both directions)
+constexpr int CH_STG_BYTES = 32 * CH_STG_ROW;      // per epilogue warp
+constexpr int CH_SMEM = CH_STAGES * CH_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 8 /*row partials*/ + 3 * CH_BN * 4 /*column params*/ +
+                        8 * CH_STG_BYTES /*store staging*/;
 
 struct ChainLayer {
   const float* bias; const float* gamma; const float* beta;
@@ -79,6 +85,7 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
   float* s_bias = reinterpret_cast<float*>(row_part + 256);                                    // [256] each
   float* s_gamma = s_bias + CH_BN;
   float* s_beta = s_gamma + CH_BN;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + CH_BN);                              // [8 epilogue warps][32][80]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,14 +190,14 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
         const int row = m0 + r;
         const bool row_ok = row < p.M;
         if (row_ok && rank == 0 && half == 0) { ly.stats[(size_t)row * 2] = mean; ly.stats[(size_t)row * 2 + 1] = rstd; }
-#pragma unroll
+        uint8_t* stg = s_stage + (warp - 2) * CH_STG_BYTES;
+        const int srow = lane >> 2, spiece = lane & 3;              // copy-out mapping: 8 rows x four 16-byte pieces per instruction
+#pragma unroll 1
         for (int cb = 0; cb < 128; cb += 32) {
           uint32_t v[32];
           tmem_ld32(tcol + (uint32_t)cb, v);
-          if (!row_ok) continue;
           const int cc = half * 128 + cb;
-          __nv_bfloat16* po = ly.pre + (size_t)row * ly.ldpre + n0 + cc;
-          __nv_bfloat16* yo = ly.y + (size_t)row * ly.ldy + n0 + cc;
+          uint4 pk[4], yk[4];
 #pragma unroll
           for (int q = 0; q < 32; q += 8) {
             float x[8], o[8];
@@ -200,17 +207,31 @@ mlp_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p
               const float a = (x[e] - mean) * rstd * s_gamma[cc + q + e] + s_beta[cc + q + e];
               o[e] = p.act == GENRL_ACT_SILU ? silu_t<true>(a) : a;
             }
-            uint4 pk, yk;
             __nv_bfloat162 a0 = __floats2bfloat162_rn(x[0], x[1]), a1 = __floats2bfloat162_rn(x[2], x[3]);
             __nv_bfloat162 a2 = __floats2bfloat162_rn(x[4], x[5]), a3 = __floats2bfloat162_rn(x[6], x[7]);
-            pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
-            pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+            pk[q >> 3].x = *reinterpret_cast<uint32_t*>(&a0); pk[q >> 3].y = *reinterpret_cast<uint32_t*>(&a1);
+            pk[q >> 3].z = *reinterpret_cast<uint32_t*>(&a2); pk[q >> 3].w = *reinterpret_cast<uint32_t*>(&a3);
             __nv_bfloat162 b0 = __floats2bfloat162_rn(o[0], o[1]), b1 = __floats2bfloat162_rn(o[2], o[3]);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(o[4], o[5]), b3 = __floats2bfloat162_rn(o[6], o[7]);
-            yk.x = *reinterpret_cast<uint32_t*>(&b0); yk.y = *reinterpret_cast<uint32_t*>(&b1);
-            yk.z = *reinterpret_cast<uint32_t*>(&b2); yk.w = *reinterpret_cast<uint32_t*>(&b3);
-            *reinterpret_cast<uint4*>(po + q) = pk;
-            *reinterpret_cast<uint4*>(yo + q) = yk;
+            yk[q >> 3].x = *reinterpret_cast<uint32_t*>(&b0); yk[q >> 3].y = *reinterpret_cast<uint32_t*>(&b1);
+            yk[q >> 3].z = *reinterpret_cast<uint32_t*>(&b2); yk[q >> 3].w = *reinterpret_cast<uint32_t*>(&b3);
+          }
+          // transpose through the warp's staging buffer: row-per-lane in, 8 rows x 64 bytes per instruction out
+#pragma unroll
+          for (int arr = 0; arr < 2; ++arr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg + lane * CH_STG_ROW + q * 16) = arr == 0 ? pk[q] : yk[q];
+            __syncwarp();
+            __nv_bfloat16* base = arr == 0 ? ly.pre : ly.y;
+            const long long ld = arr == 0 ? ly.ldpre : ly.ldy;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + srow;
+              const uint4 w = *reinterpret_cast<const uint4*>(stg + rr * CH_STG_ROW + spiece * 16);
+              const int grow = m0 + quarter * 32 + rr;
+              if (grow < p.M) *reinterpret_cast<uint4*>(base + (size_t)grow * ld + n0 + cc + spiece * 8) = w;
+            }
+            __syncwarp();
           }
         }
         ch_fence_proxy_async_global();                // the next layer's TMA loads (any CTA of the cluster) must see these stores

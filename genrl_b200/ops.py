@@ -434,10 +434,11 @@ def mlp_chain_fwd(x, weights, biases, gammas, betas, eps, act, pre, y, stats):
     ldw = (ctypes.c_longlong * L)(*[_ld(w) for w in weights])
     ldpre, ldy = _ld(pre[0]), _ld(y[0])
     assert all(_ld(t) == ldpre for t in pre) and all(_ld(t) == ldy for t in y)
-    lib.genrl_mlp_chain_fwd(_st(), M, N, L, _p(x), _ld(x), K0, _ptr_array([_p(w) for w in weights]), ldw,
-                            _ptr_array([_p(b) for b in biases]), _ptr_array([_p(g) for g in gammas]), _ptr_array([_p(b) for b in betas]),
-                            float(eps), int(act), _ptr_array([_p(t) for t in pre]), ldpre, _ptr_array([_p(t) for t in y]), ldy,
-                            _ptr_array([_p(t) for t in stats]))
+    args = (_st(), M, N, L, _p(x), _ld(x), K0, _ptr_array([_p(w) for w in weights]), ldw,
+            _ptr_array([_p(b) for b in biases]), _ptr_array([_p(g) for g in gammas]), _ptr_array([_p(b) for b in betas]),
+            float(eps), int(act), _ptr_array([_p(t) for t in pre]), ldpre, _ptr_array([_p(t) for t in y]), ldy,
+            _ptr_array([_p(t) for t in stats]))
+    lib.genrl_mlp_chain_fwd(*args)
 
 
 class _LinearLnAct(Function):

@@ -597,7 +597,8 @@ def test_vlm_reward_alignment_and_gradient(dtype, T, N, E, align):
     assert (pa_d.grad.float().cpu() - pa_r.grad).abs().max() <= tol * gscale + (1e-6 if dtype == torch.float32 else 1e-2 * gscale)
 
 
-@pytest.mark.parametrize("M,K0,N,L", [(2400, 2048, 1024, 4), (300, 1034, 1024, 1), (128, 256, 256, 3), (5000, 512, 512, 2), (77, 1024, 768, 2)])
+@pytest.mark.parametrize("M,K0,N,L", [(2400, 2048, 1024, 4), (300, 1034, 1024, 1), (128, 256, 256, 3), (5000, 512, 512, 2), (77, 1024, 768, 2),
+                                      (5000, 1034, 1024, 2), (513, 1024, 1024, 3), (8192, 1024, 1024, 1)])
 def test_mlp_chain_fwd_matches_layerwise_reference(M, K0, N, L):
     """persistent cluster chain kernel (csrc/mlp_chain.cu) vs fp32 torch on the same bf16 operands, layer by layer: pre-activations,
     (mean, rstd), activations; each layer's reference consumes the KERNEL's previous activation so that errors do not compound"""

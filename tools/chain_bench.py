@@ -1,4 +1,4 @@
-"""Chain kernel (csrc/mlp_chain.cu) vs separate GEMM + LayerNorm launches, per shape, back-to-back launches between CUDA events."""
+"""Chain kernel (csrc/mlp_chain.cu) vs separate GEMM + LayerNorm launches, per shape, CUDA graphs of back-to-back launches between CUDA events."""
 import os, sys, math
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,16 +12,23 @@ R = int(os.environ.get("REPS", "20"))
 
 
 def timeit(fn):
+    """CUDA graph of R back-to-back launches (no host time between them), replayed 3 times"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(R):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(R):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / R * 1e3
+    return e0.elapsed_time(e1) / (3 * R) * 1e3
 
 
 with ops.use_dtype(torch.bfloat16):
