@@ -15,8 +15,7 @@
 //     for the HBM latency without any software pipeline beyond the unrolled prefetch;
 //   * LayerNorm(3D) statistics via per-CTA partials + grid barrier (as in rssm_scan.cu), gates for the owned units, h_t written
 //     to L2 as bf16 (already multiplied by the next step's reset mask), second grid barrier, every CTA reloads the 16 x D operand.
-// Forward only: the backward of this shape runs step by step on the GRU-gate and GEMM kernels (ops._GruScanStream.backward), with
-// the weight gradient deferred to one GEMM over all B*T rows.
+// The backward (second kernel below) streams the transposed matrix the same way; the weight gradient is one GEMM over all B*T rows afterwards.
 #include "common.cuh"
 #include <stdlib.h>
 #include <algorithm>
@@ -236,6 +235,199 @@ __global__ void __launch_bounds__(SS_THREADS, 1) rssm_scan_stream_fwd_kernel(Str
   }
 }
 
+// =================================================================================================
+// Backward of the same time loop, weights streamed once per step as well.  CTA c owns the same 32 hidden units.  Per step t = T-1..0:
+//   A. gate + LayerNorm backward for the owned units (dh_t = external gradient + carry): the three gate gradients times gamma, x-hat, the
+//      direct path (1 - u) dh; per-CTA partial sums of the LayerNorm backward's two row reductions -> grid barrier -> dz_t (bf16, global:
+//      all CTAs need all of it, and the deferred W_h / W_x weight gradients read it afterwards);
+//   B. carry[b, k] = m_t ((1 - u) dh + sum_j dz_t[b, j] W_h[j, k]) for the owned k: the TRANSPOSED recurrent matrix (bf16 [D, 3D], built
+//      once per backward by the caller) is the streamed M operand (32 rows = two m16 tiles, K = 3D split over 16 warps), dz_t rows are the
+//      N operand, read as fragments straight from L2.
+// =================================================================================================
+constexpr int SB_WARPS = 16;
+constexpr int SB_THREADS = SB_WARPS * 32;   // 512
+constexpr int SB_ULD = SS_U + 1;
+
+struct StreamBwdParams {
+  int B, T, D, G;
+  int res_blk;
+  const float* dh_ext;                          // [B*T, D]
+  const __nv_bfloat16* z; long long ld_z;       // [B*T, 3D]
+  const float* stats;                           // [B*T, 2]
+  const __nv_bfloat16* WhT; long long ldwt;     // [D, 3D]: WhT[k][j] = W_h[j][k]
+  const float* gamma; const float* beta;
+  const float* mask;                            // [B*T] or null
+  const float* deter;                           // [B*T, D]
+  const float* h0;                              // [B, D] or null
+  __nv_bfloat16* dz; long long ld_dz;           // [B*T, 3D] out
+  float* dh0;                                   // [B, D] or null
+  float* dgamma; float* dbeta;                  // [3D] accumulated (+=), or null
+  float2* part;
+  unsigned* barrier;
+};
+
+__global__ void __launch_bounds__(SB_THREADS, 1) rssm_scan_stream_bwd_kernel(StreamBwdParams p) {
+  genrl::pdl_sync();
+  extern __shared__ __align__(16) unsigned char ss_smem[];
+  const int D = p.D, D3 = 3 * p.D, B = p.B, T = p.T, G = p.G;
+  float* red = reinterpret_cast<float*>(ss_smem);              // [16 K parts][16 b][ULD]
+  float* gs = red + SB_WARPS * SS_NB * SB_ULD;                 // [16][RLD] gamma * gate gradient
+  float* xs = gs + SS_NB * SS_RLD;                             // [16][RLD] normalised z
+  float* carry = xs + SS_NB * SS_RLD;                          // [16][U]
+  float* keep = carry + SS_NB * SS_U;                          // [16][U] (1 - u) dh
+  float* st = keep + SS_NB * SS_U;                             // [16][2] row sums / 3D
+  float* rs = st + SS_NB * 2;                                  // [16] rstd, [16] mask
+  float* dgl = rs + 2 * SS_NB;                                 // [2][R]
+  float* gb = dgl + 2 * SS_R;                                  // [2][R]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = blockIdx.x * SS_U;
+  unsigned epoch = 0;
+  for (int r = tid; r < SS_R; r += SB_THREADS) {
+    const int gate = r / SS_U, u = r % SS_U;
+    gb[r] = p.gamma[gate * D + j0 + u];
+    gb[SS_R + r] = p.beta[gate * D + j0 + u];
+    dgl[r] = 0.f; dgl[SS_R + r] = 0.f;
+  }
+  for (int i = tid; i < SS_NB * SS_U; i += SB_THREADS) { carry[i] = 0.f; keep[i] = 0.f; }
+  for (int i = tid; i < SS_NB * SS_RLD; i += SB_THREADS) { gs[i] = 0.f; xs[i] = 0.f; }
+  __syncthreads();
+
+  const int g = lane >> 2, q = lane & 3;
+  const int KP = D3 / SB_WARPS;                               // K range of a warp (multiple of 32)
+  const int nblk = KP >> 5;
+  const uint4* w_r[4];                                        // rows g, g + 8, 16 + g, 24 + g of the owned slice of W_h^T
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w_r[i] = reinterpret_cast<const uint4*>(p.WhT + (size_t)(j0 + i * 8 + g) * p.ldwt + warp * KP + q * 8);
+  uint64_t pol_keep, pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- A. gate + LayerNorm backward of the owned units ----
+    {
+      const int b = tid / SS_U, u = tid % SS_U, j = j0 + u;     // 512 threads = 16 rows x 32 units
+      if (b < B) {
+        const size_t n = (size_t)b * T + t;
+        const float mean = p.stats[n * 2], rstd = p.stats[n * 2 + 1];
+        const float m = p.mask ? p.mask[n] : 1.f;
+        const float hp = (t == 0 ? (p.h0 ? p.h0[(size_t)b * D + j] : 0.f) : p.deter[(n - 1) * D + j]) * m;
+        const float dh = p.dh_ext[n * D + j] + carry[tid];
+        const __nv_bfloat16* zr = p.z + n * p.ld_z;
+        const float xr = (__bfloat162float(zr[j]) - mean) * rstd, xc = (__bfloat162float(zr[D + j]) - mean) * rstd,
+                    xu = (__bfloat162float(zr[2 * D + j]) - mean) * rstd;
+        const float pr = xr * gb[u] + gb[SS_R + u], pc = xc * gb[SS_U + u] + gb[SS_R + SS_U + u], pu = xu * gb[2 * SS_U + u] + gb[SS_R + 2 * SS_U + u];
+        const float r = sigmoidf_(pr), cand = tanhf(r * pc), uu = sigmoidf_(pu - 1.0f);
+        const float drc = dh * uu * (1.0f - cand * cand);
+        const float gpr = drc * pc * r * (1.0f - r), gpc = drc * r, gpu = dh * (cand - hp) * uu * (1.0f - uu);
+        float* gr = gs + b * SS_RLD; float* xr_ = xs + b * SS_RLD;
+        gr[u] = gpr * gb[u]; gr[SS_U + u] = gpc * gb[SS_U + u]; gr[2 * SS_U + u] = gpu * gb[2 * SS_U + u];
+        xr_[u] = xr; xr_[SS_U + u] = xc; xr_[2 * SS_U + u] = xu;
+        keep[tid] = dh * (1.0f - uu);
+        if (u == 0) { rs[b] = rstd; rs[SS_NB + b] = m; }
+        if (p.dgamma) {
+          atomicAdd(&dgl[u], gpr * xr); atomicAdd(&dgl[SS_U + u], gpc * xc); atomicAdd(&dgl[2 * SS_U + u], gpu * xu);
+          atomicAdd(&dgl[SS_R + u], gpr); atomicAdd(&dgl[SS_R + SS_U + u], gpc); atomicAdd(&dgl[SS_R + 2 * SS_U + u], gpu);
+        }
+      }
+    }
+    __syncthreads();
+    if (warp < B) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < SS_R / 32; ++k) { const float gv = gs[warp * SS_RLD + lane + 32 * k]; s1 += gv; s2 = fmaf(gv, xs[warp * SS_RLD + lane + 32 * k], s2); }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) p.part[(size_t)warp * G + blockIdx.x] = make_float2(s1, s2);
+    }
+    ss_grid_barrier(p.barrier, epoch, G);
+    if (warp < B) {
+      constexpr int NC = SS_MAX_CTAS / 32;
+      float2 v[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) { const int c = lane + 32 * k; v[k] = c < G ? __ldcg(p.part + (size_t)warp * G + c) : make_float2(0.f, 0.f); }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NC; ++k) { s1 += v[k].x; s2 += v[k].y; }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) { st[warp * 2] = s1 / D3; st[warp * 2 + 1] = s2 / D3; }
+    }
+    __syncthreads();
+    for (int i = tid; i < SS_NB * SS_R; i += SB_THREADS) {
+      const int b = i / SS_R, r = i % SS_R;
+      if (b < B) {
+        const float dzv = rs[b] * (gs[b * SS_RLD + r] - st[b * 2] - xs[b * SS_RLD + r] * st[b * 2 + 1]);
+        p.dz[((size_t)b * T + t) * p.ld_dz + (r / SS_U) * D + j0 + (r % SS_U)] = __float2bfloat16_rn(dzv);
+      }
+    }
+    ss_grid_barrier(p.barrier, epoch, G);
+    // ---- B. carry = m_t ((1 - u) dh + dz_t W_h[:, owned units]) ----
+    {
+      float acc[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) { acc[a][c][0] = 0.f; acc[a][c][1] = 0.f; acc[a][c][2] = 0.f; acc[a][c][3] = 0.f; }
+      const uint4* d_r[2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int b = nt * 8 + g;
+        d_r[nt] = b < B ? reinterpret_cast<const uint4*>(p.dz + ((size_t)b * T + t) * p.ld_dz + warp * KP + q * 8) : nullptr;
+      }
+      constexpr int PF = 3;
+      for (int blk0 = 0; blk0 < nblk; blk0 += PF) {
+        uint4 w[PF][4], dv[PF][2];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          if (blk0 + i < nblk) {
+            const uint64_t pol = (blk0 + i) < p.res_blk ? pol_keep : pol_stream;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[i][k] = ss_ld_policy(w_r[k] + (blk0 + i) * 4, pol);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) dv[i][nt] = d_r[nt] ? __ldcg(d_r[nt] + (blk0 + i) * 4) : zero4;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          if (blk0 + i >= nblk) break;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              ss_mma(acc[mt][nt], w[i][2 * mt].x, w[i][2 * mt + 1].x, w[i][2 * mt].y, w[i][2 * mt + 1].y, dv[i][nt].x, dv[i][nt].y);
+              ss_mma(acc[mt][nt], w[i][2 * mt].z, w[i][2 * mt + 1].z, w[i][2 * mt].w, w[i][2 * mt + 1].w, dv[i][nt].z, dv[i][nt].w);
+            }
+        }
+      }
+      // accumulator (unit row, batch column) -> red[warp][batch][unit]
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          float* rb0 = red + ((size_t)warp * SS_NB + nt * 8 + q * 2) * SB_ULD + mt * 16 + g;
+          rb0[0] = acc[mt][nt][0]; rb0[SB_ULD] = acc[mt][nt][1]; rb0[8] = acc[mt][nt][2]; rb0[SB_ULD + 8] = acc[mt][nt][3];
+        }
+    }
+    __syncthreads();
+    {
+      const int b = tid / SS_U, u = tid % SS_U;
+      float sum = keep[tid];
+#pragma unroll
+      for (int k = 0; k < SB_WARPS; ++k) sum += red[((size_t)k * SS_NB + b) * SB_ULD + u];
+      const float cv = b < B ? sum * rs[SS_NB + b] : 0.f;
+      carry[tid] = cv;
+      if (t == 0 && p.dh0 && b < B) p.dh0[(size_t)b * D + j0 + u] = cv;
+    }
+    __syncthreads();
+  }
+  if (p.dgamma) {
+    for (int r = tid; r < SS_R; r += SB_THREADS) {
+      const int gate = r / SS_U, u = r % SS_U;
+      atomicAdd(&p.dgamma[gate * D + j0 + u], dgl[r]);
+      atomicAdd(&p.dbeta[gate * D + j0 + u], dgl[SS_R + r]);
+    }
+  }
+}
+
 }  // namespace genrl
 
 using namespace genrl;
@@ -283,4 +475,38 @@ extern "C" int genrl_rssm_scan_stream_fwd(void* stream, int B, int T, int D, con
   e = cudaLaunchCooperativeKernel((void*)rssm_scan_stream_fwd_kernel, dim3(p.G), dim3(SS_THREADS), args, smem, st);
   GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_stream_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
   return check_launch("rssm_scan_stream_fwd");
+}
+
+// Backward of genrl_rssm_scan_stream_fwd: dz (bf16 [B*T, 3D]) = gradient of the pre-LayerNorm GRU activations, dh0, dgamma / dbeta (+=).
+// WhT: the TRANSPOSED recurrent matrix in bf16, [D, 3D] with row stride ldwt.  Requires D % 512 == 0 (returns 2 otherwise: the caller then
+// walks the steps with genrl_gru_bwd + genrl_gemm).
+extern "C" int genrl_rssm_scan_stream_bwd(void* stream, int B, int T, int D, const float* dh_ext, const void* z, long long ld_z, const float* stats,
+                                          const void* WhT, long long ldwt, const float* gamma, const float* beta, const float* mask,
+                                          const float* deter, const float* h0, void* dz, long long ld_dz, float* dh0, float* dgamma, float* dbeta,
+                                          void* workspace) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (genrl_rssm_scan_stream_supported(B, D) != 1 || (3 * D / SB_WARPS) % 32 != 0) return 2;
+  GENRL_REQUIRE(T >= 1 && ldwt % 8 == 0 && ld_dz % 8 == 0 && ((reinterpret_cast<uintptr_t>(WhT) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0,
+                "rssm_scan_stream_bwd: W_h^T / dz rows must be 16-byte aligned");
+  StreamBwdParams p;
+  p.B = B; p.T = T; p.D = D; p.G = D / SS_U;
+  {
+    const double wbytes = 3.0 * D * D * 2.0;
+    int pct = (int)std::min(100.0, 100.0 * 75e6 / wbytes);
+    if (const char* e = getenv("GENRL_SCAN_STREAM_RES")) pct = atoi(e);
+    p.res_blk = (int)((long long)(3 * D / SB_WARPS / 32) * pct / 100);
+  }
+  p.dh_ext = dh_ext; p.z = reinterpret_cast<const __nv_bfloat16*>(z); p.ld_z = ld_z; p.stats = stats;
+  p.WhT = reinterpret_cast<const __nv_bfloat16*>(WhT); p.ldwt = ldwt; p.gamma = gamma; p.beta = beta; p.mask = mask; p.deter = deter; p.h0 = h0;
+  p.dz = reinterpret_cast<__nv_bfloat16*>(dz); p.ld_dz = ld_dz; p.dh0 = dh0; p.dgamma = dgamma; p.dbeta = dbeta;
+  p.barrier = reinterpret_cast<unsigned*>(workspace);
+  p.part = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + SS_FLAG_BYTES);
+  const size_t smem = ((size_t)SB_WARPS * SS_NB * SB_ULD + 2 * SS_NB * SS_RLD + 2 * SS_NB * SS_U + SS_NB * 2 + 2 * SS_NB + 4 * SS_R) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(rssm_scan_stream_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_stream_bwd: smem attribute: %s", cudaGetErrorString(e));
+  cudaMemsetAsync(workspace, 0, SS_FLAG_BYTES, st);
+  void* args[] = {&p};
+  e = cudaLaunchCooperativeKernel((void*)rssm_scan_stream_bwd_kernel, dim3(p.G), dim3(SB_THREADS), args, smem, st);
+  GENRL_REQUIRE(e == cudaSuccess, "rssm_scan_stream_bwd: cooperative launch failed: %s", cudaGetErrorString(e));
+  return check_launch("rssm_scan_stream_bwd");
 }

@@ -1234,8 +1234,9 @@ def _gru_scan_stepwise(gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
 
 class _GruScanStream(Function):
     """The same recurrence for hidden sizes whose W_h cannot stay resident in shared memory (BASELINE configs[4], D = 4096): the forward is ONE
-    persistent cooperative kernel that streams the bf16 weights once per time step (csrc/rssm_scan_stream.cu); the backward walks the steps with
-    the GRU-gate backward kernel and one M = B dgrad GEMM per step, the W_h gradient is one GEMM over all B*T rows afterwards."""
+    persistent cooperative kernel that streams the bf16 weights once per time step (csrc/rssm_scan_stream.cu), the backward a second one that
+    streams the transposed matrix (D % 512 == 0; other sizes walk the steps with the GRU-gate backward kernel and one M = B dgrad GEMM per
+    step); the W_h gradient is one GEMM over all B*T rows afterwards."""
 
     @staticmethod
     def forward(ctx, gx, w_gru, gamma, beta, mask, h0, B, T, Hd):
@@ -1274,8 +1275,23 @@ class _GruScanStream(Function):
             if train:
                 gb, dg = _grad_buf(ctx.gamma)
                 bb, db = _grad_buf(ctx.beta)
+            dh0 = None
+            want_dh0 = h0c is not None and ctx.needs_input_grad[5]
+            # one persistent kernel that streams W_h^T once per step (csrc/rssm_scan_stream.cu); 2 = shape not eligible -> step by step below
+            rc = 2
+            if D % 512 == 0:
+                wht = wh.t().contiguous()
+                dh0_buf = torch.empty(B, D, device=dev, dtype=torch.float32) if want_dh0 else None
+                rc = lib.load().genrl_rssm_scan_stream_bwd(_st(), B, T, D, _p(dd3), _p(z), 3 * D, _p(stats), _p(wht), 3 * D, _p(ctx.gamma),
+                                                           _p(ctx.beta), _p(mask), _p(deter), _p(h0c), _p(dz), 3 * D, _p(dh0_buf), _p(gb), _p(bb),
+                                                           _p(_scan_workspace(B, T, D, dev)))
+            if rc == 0:
+                lib.launches += 1
+                dh0 = dh0_buf
+            elif rc != 2:
+                raise GenrlError(f"genrl_rssm_scan_stream_bwd failed: {lib.load().genrl_last_error().decode()}")
             carry = None
-            for t in range(T - 1, -1, -1):
+            for t in (range(T - 1, -1, -1) if rc == 2 else ()):
                 dh = dd3[:, t].contiguous() if carry is None else dd3[:, t] + carry
                 hp = det3[:, t - 1] if t > 0 else (h0c if h0c is not None else torch.zeros(B, D, device=dev, dtype=torch.float32))
                 if m3 is not None:
@@ -1289,7 +1305,8 @@ class _GruScanStream(Function):
                 # d(m_t h_{t-1}) = (1 - u) dh + dz_t W_h;  times the reset mask = the gradient reaching h_{t-1}
                 gemm(dzt, wh, out=dhp, trans_w=True, accumulate=True)
                 carry = dhp if m3 is None else dhp * m3[:, t]
-            dh0 = carry if (h0c is not None and ctx.needs_input_grad[5]) else None
+            if rc == 2:
+                dh0 = carry if want_dh0 else None
             dw = None
             if train:
                 gbuf, dw_ret = _grad_buf(w)

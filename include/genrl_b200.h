@@ -195,9 +195,13 @@ int genrl_rssm_scan_bwd(void* stream, int B, int T, int D, const float* dh_ext, 
 
 /* Weight-streaming variant of the same time loop for hidden sizes whose recurrent matrix cannot stay resident in shared memory
  * (BASELINE configs[4]: deter = 4096): W_h (bf16 [3D, D], row stride ldw) is streamed from L2 / HBM once per time step straight into
- * mma.sync A fragments, the <= 16 batch rows are the N operand.  Forward only (the backward of this shape runs step by step on
- * genrl_gru_bwd + genrl_gemm).  hprev / z: bf16 outputs [B*T, D] / [B*T, 3D]; workspace as for genrl_rssm_scan_fwd. */
+ * mma.sync A fragments, the <= 16 batch rows are the N operand.  hprev / z: bf16 outputs [B*T, D] / [B*T, 3D]; workspace as for genrl_rssm_scan_fwd. */
 int genrl_rssm_scan_stream_supported(int B, int D);      /* 1 / 0, no launch */
+/* backward: dz (bf16 [B*T, 3D]) = gradient of the pre-LayerNorm activations; WhT = TRANSPOSED recurrent matrix, bf16 [D, 3D]; returns 2 when
+ * D % 512 != 0 (the caller then walks the steps with genrl_gru_bwd + genrl_gemm) */
+int genrl_rssm_scan_stream_bwd(void* stream, int B, int T, int D, const float* dh_ext, const void* z, long long ld_z, const float* stats,
+                               const void* WhT, long long ldwt, const float* gamma, const float* beta, const float* mask, const float* deter,
+                               const float* h0, void* dz, long long ld_dz, float* dh0, float* dgamma, float* dbeta, void* workspace);
 int genrl_rssm_scan_stream_fwd(void* stream, int B, int T, int D, const float* gx, const void* Wh, long long ldw, const float* gamma,
                                const float* beta, const float* mask, const float* h0, float* deter, void* hprev, long long ld_hp,
                                void* z, long long ld_z, float* stats, void* workspace);

@@ -33,6 +33,18 @@ def run(B, T, D, Hd, reps=5):
                 e1.record()
                 torch.cuda.synchronize()
             out[name] = e0.elapsed_time(e1) * 1e3 / reps
+            # forward + backward (dgx, dW_h, dgamma / dbeta, dh0)
+            gxg = gx.clone().requires_grad_(True)
+            dd = torch.randn(B * T, D, device=DEV)
+            for k in range(reps + 1):
+                if k == 1:
+                    torch.cuda.synchronize()
+                    e0.record()
+                w.grad = g.grad = b.grad = gxg.grad = None
+                ops.gru_scan(gxg, w, g, b, mask, h0, B, T, Hd).backward(dd)
+            e1.record()
+            torch.cuda.synchronize()
+            out[name + " fwd+bwd"] = e0.elapsed_time(e1) * 1e3 / reps
         wbytes = 3 * D * D * 2
         for name, us in out.items():
             print(f"B={B} T={T} D={D}  {name:9s} forward {us:9.1f} us  = {us / T:7.2f} us/step  weights {wbytes / 1e6:.0f} MB/step -> {wbytes / (us / T) / 1e3:7.0f} GB/s")
