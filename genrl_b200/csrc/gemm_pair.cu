@@ -33,6 +33,8 @@ constexpr int PR_SMEM = PR_STAGES * PR_STAGE_BYTES + 1024 + 512;
 
 struct PairParams {
   int M, N, K, num_kb;
+  int splits, kb_per_split;      // split-K: work item w = tile * splits + split covers k-blocks [split * kb_per_split, ...); splits > 1 -> atomic epilogue
+  int atomic;                    // fp32 atomicAdd epilogue (C += result: the wgrad GEMMs accumulate into the flat gradient buffers)
   int ldc, c_dtype;
   const float* bias;
   void* C;
@@ -72,7 +74,7 @@ __device__ __forceinline__ void pr_mbar_arrive_cluster(uint32_t bar_cluster_addr
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
-template <bool B_MN>
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(PR_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +94,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int nkb = p.num_kb;
   const int tiles_n = (p.N + PR_BN - 1) / PR_BN;
   const int tiles = ((p.M + 2 * PR_BM - 1) / (2 * PR_BM)) * tiles_n;
+  const int items = tiles * p.splits;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -115,16 +118,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < tiles; t += npairs) {
+      for (int w = pair; w < items; w += npairs) {
+        const int t = w / p.splits, sp = w - t * p.splits;
         const int m0 = (t / tiles_n) * (2 * PR_BM) + (int)rank * PR_BM;
         const int n0 = (t % tiles_n) * PR_BN + (int)rank * (PR_BN / 2);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
           uint8_t* sa = smem + stage * PR_STAGE_BYTES;
           uint8_t* sb = sa + PR_A_BYTES;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * PR_STAGE_BYTES);
           const uint32_t fb = pr_mapa(smem_u32(&full_bar[stage]), 0);
-          pr_tma_load_2d(&tmA, fb, sa, kb * PR_BK, m0);                                       // box {64 k, 128 rows}
+          if (!A_MN) {
+            pr_tma_load_2d(&tmA, fb, sa, kb * PR_BK, m0);                                     // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < PR_BM / 64; ++j)                                              // box {64 m, 64 k}
+              pr_tma_load_2d(&tmA, fb, sa + j * (64 * PR_BK * 2), m0 + 64 * j, kb * PR_BK);
+          }
           if (!B_MN) {
             pr_tma_load_2d(&tmB, fb, sb, kb * PR_BK, n0);                                     // box {64 k, 128 weight rows}
           } else {
@@ -139,27 +150,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (leader && lane == 0) {
       // M = 256 (pair), N = 256: c = F32, a = b = BF16, B major, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(PR_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(PR_BN >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = pair; t < tiles; t += npairs, ++it) {
+      for (int w = pair; w < items; w += npairs, ++it) {
+        const int sp = w % p.splits;
+        const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
         const int buf = it & 1;
         mbar_wait_sleep(&tempty_bar[buf], ((it >> 1) & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * PR_BN);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * PR_STAGE_BYTES);
           const uint32_t sb = sa + PR_A_BYTES;
 #pragma unroll
           for (int k = 0; k < PR_BK / 16; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, 64 * PR_BK * 2, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, 64 * PR_BK * 2, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            pr_umma_bf16(acc, make_smem_desc(sa + k * 32, 16, 1024), bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            pr_umma_bf16(acc, ad, bd, idesc, (kb > kb0 || k != 0) ? 1u : 0u);
           }
           pr_umma_commit_mc(&empty_bar[stage], 3);
-          if (kb == nkb - 1) pr_umma_commit_mc(&tfull_bar[buf], 3);
+          if (kb == kb1 - 1) pr_umma_commit_mc(&tfull_bar[buf], 3);
           if (++stage == PR_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -171,7 +186,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tempty_leader0 = pr_mapa(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_leader1 = pr_mapa(smem_u32(&tempty_bar[1]), 0);
     int it = 0;
-    for (int t = pair; t < tiles; t += npairs, ++it) {
+    for (int w = pair; w < items; w += npairs, ++it) {
+      const int t = w / p.splits, sp = w - t * p.splits;
       const int buf = it & 1;
       const int m0 = (t / tiles_n) * (2 * PR_BM) + (int)rank * PR_BM;
       const int n0 = (t % tiles_n) * PR_BN;
@@ -191,11 +207,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && sp == 0) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(p.bias + col0 + j);
         }
-        if (p.c_dtype == GENRL_F32) {
+        if (p.atomic) {
+          float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(out + j, f[j]);
+        } else if (p.c_dtype == GENRL_F32) {
           float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
           if (ncols == 32 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
 #pragma unroll
@@ -255,6 +275,7 @@ extern "C" int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A,
   else         { if (make_map(&tb, W, K, N, ldw, 64, 64)) return 1; }
   PairParams p;
   p.M = M; p.N = N; p.K = K; p.num_kb = ceil_div(K, PR_BK); p.ldc = (int)ldc; p.c_dtype = c_dtype; p.bias = bias; p.C = C;
+  p.splits = 1; p.kb_per_split = p.num_kb; p.atomic = 0;
   if (g_pair_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -277,12 +298,57 @@ extern "C" int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A,
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e;
   if (!transW) {
-    if (!attr_set[0]) { cudaFuncSetAttribute(gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM); attr_set[0] = true; }
-    e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<false>, ta, tb, p);
+    if (!attr_set[0]) { cudaFuncSetAttribute(gemm_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM); attr_set[0] = true; }
+    e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<false, false>, ta, tb, p);
   } else {
-    if (!attr_set[1]) { cudaFuncSetAttribute(gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM); attr_set[1] = true; }
-    e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<true>, ta, tb, p);
+    if (!attr_set[1]) { cudaFuncSetAttribute(gemm_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM); attr_set[1] = true; }
+    e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<false, true>, ta, tb, p);
   }
   GENRL_REQUIRE(e == cudaSuccess, "gemm_pair launch failed: %s", cudaGetErrorString(e));
   return check_launch("gemm_pair_kernel");
+}
+
+// Weight-gradient form on the 2-CTA kernel:  C[M,N] += A^T W  with A stored [K, M] and W stored [K, N] (K = rows of the activation slabs: both
+// operands MN-major), fp32 C, split over K so that every CTA pair has a work item; partial tiles are combined with fp32 atomics.
+// Returns 2 when the shape is not eligible.
+extern "C" int genrl_gemm_pair_wgrad(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, float* C,
+                                     long long ldc) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M % 128 != 0 || N % 128 != 0 || (lda % 8) || (ldw % 8) || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15)) return 2;
+  CUtensorMap ta, tb;
+  if (make_map(&ta, A, K, M, lda, 64, 64)) return 1;
+  if (make_map(&tb, W, K, N, ldw, 64, 64)) return 1;
+  if (g_pair_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_pair_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_pair_sms <= 0) g_pair_sms = 148;
+  }
+  PairParams p;
+  p.M = M; p.N = N; p.K = K; p.num_kb = ceil_div(K, PR_BK); p.ldc = (int)ldc; p.c_dtype = GENRL_F32; p.bias = nullptr; p.C = C;
+  const int tiles = ceil_div(M, 2 * PR_BM) * ceil_div(N, PR_BN);
+  const int max_pairs = g_pair_sms / 2;
+  // as many K splits as keep every pair busy, each split at least 16 k-blocks long
+  int splits = std::max(1, std::min(max_pairs / std::max(tiles, 1), p.num_kb / 16));
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.splits = splits; p.atomic = 1;
+  const int npairs = std::min(tiles * splits, max_pairs);
+  static bool attr_set = false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs, 1, 1);
+  cfg.blockDim = dim3(PR_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = PR_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  if (!attr_set) { cudaFuncSetAttribute(gemm_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM); attr_set = true; }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_pair_kernel<true, true>, ta, tb, p);
+  GENRL_REQUIRE(e == cudaSuccess, "gemm_pair_wgrad launch failed: %s", cudaGetErrorString(e));
+  return check_launch("gemm_pair_kernel(wgrad)");
 }

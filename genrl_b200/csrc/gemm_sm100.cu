@@ -757,6 +757,8 @@ using namespace genrl;
 extern "C" int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, int transW, void* C,
                                long long ldc, int c_dtype, const float* bias);
 
+extern "C" int genrl_gemm_pair_wgrad(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, float* C,
+                                     long long ldc);
 extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, int transA, const void* W,
                           long long ldw, int transW, int in_dtype, void* C, long long ldc, int c_dtype, const float* bias,
                           int accumulate) {
@@ -795,6 +797,15 @@ extern "C" int genrl_gemm(void* stream, int M, int N, int K, const void* A, long
       const int rc = genrl_gemm_pair(stream, M, N, K, A, lda, W, ldw, transW, C, ldc, c_dtype, bias);
       if (rc != 2) return rc;
     }
+  }
+  // weight gradients over long row slabs (C += A^T W, both operands MN-major, K = rows): the 128x128 split-K kernel moves 0.0156 operand
+  // bytes per FLOP through the L2 -> SM fabric (1024x1024x36000: 93 us = 0.81 PFLOP/s); the 2-CTA kernel needs half of that
+  static int pair_wgrad = -1;
+  if (pair_wgrad < 0) { const char* e = getenv("GENRL_GEMM_PAIR_WGRAD"); pair_wgrad = e ? atoi(e) : 1; }
+  if (pair_mode && pair_wgrad && transA && transW && accumulate && c_dtype == GENRL_F32 && bias == nullptr && M % 128 == 0 && N % 128 == 0 &&
+      (pair_wgrad == 2 || (K >= 8192 && (long long)M * N >= 512 * 512))) {
+    const int rc = genrl_gemm_pair_wgrad(stream, M, N, K, A, lda, W, ldw, reinterpret_cast<float*>(C), ldc);
+    if (rc != 2) return rc;
   }
   const bool persist_ok = !transA && !accumulate;
   // measured (tools/debug_pgemm.py): 1.02-1.15 PFLOP/s vs 0.79-1.0 for N >= 1024; N = 255 (300 tiles = 2.03 waves) loses to the 128x128 kernel

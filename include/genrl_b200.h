@@ -33,6 +33,10 @@ int genrl_gemm(void* stream, int M, int N, int K, const void* A, long long lda, 
 int genrl_gemm_pair(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, int transW, void* C,
                     long long ldc, int c_dtype, const float* bias);
 
+/* Weight-gradient form on the same kernel: C[M,N] (fp32) += A^T W with A stored [K, M] and W stored [K, N] (K = rows of the activation slabs),
+ * split over K with an fp32 atomic epilogue.  M, N multiples of 128.  Returns 2 if the shape is not eligible. */
+int genrl_gemm_pair_wgrad(void* stream, int M, int N, int K, const void* A, long long lda, const void* W, long long ldw, float* C, long long ldc);
+
 /* fp32 parity mode on the tensor cores ("bf16x3"): x = hi + mid + lo with three bf16 terms (24 significant bits); the host side runs the six
  * products a_i w_j, i + j <= 2, on the bf16 tcgen05 GEMM with fp32 accumulation into C. */
 int genrl_split3_bf16(void* stream, const float* src, long long lds, void* hi, void* mid, void* lo, long long ldd, long long rows, int cols);

@@ -562,6 +562,26 @@ def test_gru_scan_weight_streaming_matches_stepwise(B, T, D, Hd, resets, monkeyp
         close(got[0], old[0], msg="stream vs op-level deter", rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 36000), (1024, 2048, 19200), (3072, 1024, 9000), (256, 512, 8192), (128, 128, 300), (1536, 1024, 2400)])
+def test_gemm_pair_wgrad_split_k(M, N, K):
+    """weight-gradient form of the 2-CTA kernel (csrc/gemm_pair.cu: both operands MN-major, split-K, fp32 atomic epilogue): C += A^T W against
+    an fp32 matmul of the same bf16 operands, C pre-filled (accumulate), ragged last k-block"""
+    from genrl_b200._lib import lib
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(K, M, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    w = (torch.randn(K, N, generator=g) * 0.5).to(DEV, torch.bfloat16)
+    c0 = torch.randn(M, N, generator=g).to(DEV)
+    c = c0.clone()
+    rc = lib.load().genrl_gemm_pair_wgrad(ops._st(), M, N, K, a.data_ptr(), M, w.data_ptr(), N, c.data_ptr(), N)
+    assert rc == 0, lib.load().genrl_last_error()
+    ref = c0 + a.float().t() @ w.float()
+    close(c, ref, rtol=2e-3, atol=2e-2 * math.sqrt(K / 1000), msg="pair wgrad")
+    # the dispatcher sends the long-K accumulate form here and gives the same numbers as the 128x128 split-K kernel within fp32 atomics noise
+    c2 = c0.clone()
+    ops.gemm(a, w, out=c2, trans_a=True, trans_w=True, accumulate=True)
+    close(c2, ref, rtol=2e-3, atol=2e-2 * math.sqrt(K / 1000), msg="dispatched wgrad")
+
+
 @pytest.mark.parametrize("dtype,T,N,E,align", [(torch.float32, 11, 37, 96, True), (torch.float32, 16, 64, 1536, True),
                                                (torch.bfloat16, 16, 50, 1536, True), (torch.float32, 5, 9, 64, False)])
 def test_vlm_reward_alignment_and_gradient(dtype, T, N, E, align):
