@@ -65,15 +65,8 @@ __device__ __forceinline__ uint4 ss_ld_policy(const uint4* p, uint64_t pol) {
   return v;
 }
 
-// fire-and-forget prefetch of a contiguous global range into L2 (the part of the weights that is NOT kept with evict_last is pulled from HBM
-// while the step's synchronisation phase runs: grid barriers, statistics, gates — no weight load is in flight there otherwise)
-__device__ __forceinline__ void ss_prefetch_l2(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 struct StreamFwdParams {
   int B, T, D, G;
-  int prefetch;                             // 1: prefetch the streamed (evict_first) part of the next step's weights into L2 after the product
   int res_blk;                              // K blocks (of 32) per K part loaded with the evict_last policy
   const float* gx;                          // [B*T, 3D] x-part of the GRU pre-activation (row n = b*T + t)
   const __nv_bfloat16* Wh; long long ldw;   // W_gru[:, Hd:] in bf16: 3D rows, row stride ldw
@@ -181,10 +174,6 @@ __global__ void __launch_bounds__(SS_THREADS, 1) rssm_scan_stream_fwd_kernel(Str
         }
       }
     }
-    if (p.prefetch && t + 1 < T && tid < SS_R * SS_KP && p.res_blk < nblk) {
-      const int r = tid % SS_R, kpp = tid / SS_R;
-      ss_prefetch_l2(p.Wh + (size_t)((r / SS_U) * D + j0 + (r % SS_U)) * p.ldw + kpp * KQ + p.res_blk * 32, (uint32_t)(nblk - p.res_blk) * 64u);
-    }
     // accumulator (weight row, batch column) -> red[kp][batch][row]
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
@@ -261,7 +250,6 @@ constexpr int SB_ULD = SS_U + 1;
 
 struct StreamBwdParams {
   int B, T, D, G;
-  int prefetch;
   int res_blk;
   const float* dh_ext;                          // [B*T, D]
   const __nv_bfloat16* z; long long ld_z;       // [B*T, 3D]
@@ -410,10 +398,6 @@ __global__ void __launch_bounds__(SB_THREADS, 1) rssm_scan_stream_bwd_kernel(Str
             }
         }
       }
-      if (p.prefetch && t > 0 && p.res_blk < nblk) {               // 32 rows x 16 K parts = 512 segments: one per thread
-        const int r = tid % SS_U, kpp = tid / SS_U;
-        ss_prefetch_l2(p.WhT + (size_t)(j0 + r) * p.ldwt + kpp * KP + p.res_blk * 32, (uint32_t)(nblk - p.res_blk) * 64u);
-      }
       // accumulator (unit row, batch column) -> red[warp][batch][unit]
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -477,8 +461,6 @@ extern "C" int genrl_rssm_scan_stream_fwd(void* stream, int B, int T, int D, con
     int pct = (int)std::min(100.0, 100.0 * 75e6 / wbytes);
     if (const char* e = getenv("GENRL_SCAN_STREAM_RES")) pct = atoi(e);
     p.res_blk = (int)((long long)(D / SS_KP / 32) * pct / 100);
-    const char* pf = getenv("GENRL_SCAN_STREAM_PREFETCH");
-    p.prefetch = (pf && pf[0] == '0') ? 0 : 1;
   }
   p.gx = gx; p.Wh = reinterpret_cast<const __nv_bfloat16*>(Wh); p.ldw = ldw; p.gamma = gamma; p.beta = beta; p.mask = mask; p.h0 = h0;
   p.deter = deter; p.hprev = reinterpret_cast<__nv_bfloat16*>(hprev); p.ld_hp = ld_hp; p.z = reinterpret_cast<__nv_bfloat16*>(z); p.ld_z = ld_z;
@@ -513,8 +495,6 @@ extern "C" int genrl_rssm_scan_stream_bwd(void* stream, int B, int T, int D, con
     int pct = (int)std::min(100.0, 100.0 * 75e6 / wbytes);
     if (const char* e = getenv("GENRL_SCAN_STREAM_RES")) pct = atoi(e);
     p.res_blk = (int)((long long)(3 * D / SB_WARPS / 32) * pct / 100);
-    const char* pf = getenv("GENRL_SCAN_STREAM_PREFETCH");
-    p.prefetch = (pf && pf[0] == '0') ? 0 : 1;
   }
   p.dh_ext = dh_ext; p.z = reinterpret_cast<const __nv_bfloat16*>(z); p.ld_z = ld_z; p.stats = stats;
   p.WhT = reinterpret_cast<const __nv_bfloat16*>(WhT); p.ldwt = ldwt; p.gamma = gamma; p.beta = beta; p.mask = mask; p.deter = deter; p.h0 = h0;
