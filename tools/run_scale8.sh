@@ -14,8 +14,7 @@ except Exception as e:
     print("$tag failed", e)
 PY
 }
-run default GENRL_X=0
-run nccl_info NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL
-grep -h -o "NVLS[^ ]*\|Ring [0-9]*\|Connected NVLS\|NVLS comm" gpurun_out/r02b_bench_8gpu_nccl_info.err | sort | uniq -c | head -8
+run default NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT
+grep -h -i -o "nvls[a-z ]*\|[0-9]* coll channels\|[0-9]* nvls channels" gpurun_out/r02b_bench_8gpu_default.err | sort | uniq -c | sort -rn | head -8
 run early_cta8 GENRL_DP_EARLY=1 NCCL_MAX_CTAS=8
 run cta8 NCCL_MAX_CTAS=8
