@@ -17,6 +17,8 @@ class DataParallel:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.nccl = dist.get_backend(group) == "nccl"
+        import os
+        self.bf16_transport = os.environ.get("GENRL_DP_BF16", "0") == "1"
         self.n_allreduce = 0
         self.bytes_allreduced = 0
 
@@ -27,7 +29,12 @@ class DataParallel:
         if self.world == 1:
             return
         for g in flats:
-            if self.nccl and g.is_cuda:
+            if self.nccl and g.is_cuda and self.bf16_transport and g.dtype == torch.float32:
+                # half the bytes on the wire: round to bf16 (nearest even, unbiased), average, widen again (GENRL_DP_BF16=1)
+                h = g.to(torch.bfloat16)
+                dist.all_reduce(h, op=dist.ReduceOp.AVG, group=self.group)
+                g.copy_(h)
+            elif self.nccl and g.is_cuda:
                 dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)

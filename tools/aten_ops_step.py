@@ -7,7 +7,7 @@ from genrl_b200.agent.genrl import GenRLAgent
 from torch.profiler import profile, ProfilerActivity
 
 class A: pass
-args = A(); args.batch, args.length, args.horizon, args.action_dim = 50, 48, 15, 10
+args = A(); args.batch, args.length, args.horizon, args.action_dim, args.sequence, args.preset = 50, 48, 15, 10, "S2", "c2"
 cfg, obs_space, act_spec = bench.make_cfg(args, "cuda:0", 16)
 torch.manual_seed(1)
 with contextlib.redirect_stdout(io.StringIO()):
