@@ -493,7 +493,9 @@ def roofline_pass(step, devb, nb, lib, args, agent, ms_step):
         achieved = counts["gemm_flops"] * n / (alone_us * 1e-6) / 1e12 if alone_us else in_step
         peak = pk["tf_sustained"] if bf16 else 75.0
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r02b_gemm_traffic.json")          # ncu pass of the second half of round 2
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
         if not os.path.exists(tpath):
             tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
         if bf16 and os.path.exists(tpath):

@@ -23,6 +23,7 @@ constexpr int CV_THREADS = 192;
 constexpr int CV_GATHER = 128;     // gather threads of the wgrad kernel (warps 2..5)
 constexpr int CVF_GATHER = 256;    // gather threads of the forward kernel (warps 2..9)
 constexpr int CV_LAG = 2;          // cp.async groups kept in flight per gather thread before the stage is published
+constexpr int CVF_KTAB_KB = 32;    // k-blocks covered by the forward kernel's shared-memory k table (8 entries of 8 bytes per k-block)
 
 // .ca: every input pixel is gathered by several taps of the same CTA (4 for k4/s2, 9 for the 3x3 sub-pixel taps); the CTA's input
 // footprint (~20 KB) stays in L1, so the re-reads do not go back to L2
@@ -51,6 +52,7 @@ struct ConvGeom {
   int K;                     // th*tw*C
   long long rows;            // Nimg*RH*RW
   unsigned long long m_rhw, m_rw, m_c, m_tw;   // fast_div magics for RH*RW, RW, C, tw
+  int all_inside;            // gather form whose every tap of every valid row lies inside the image (stride-2 convs without padding): constant masks
 };
 
 // row -> (n, yy, xx) of the row grid
@@ -70,6 +72,7 @@ __device__ __forceinline__ void row_state(const ConvGeom& g, long long row, int 
     decode_row(g, row, rhw, n, yy, xx);
     const int iy0 = yy * g.sy, ix0 = xx * g.sy;
     off = (int)(((n * g.IH + iy0) * g.IW + ix0) * g.C);
+    if (g.all_inside) { mask = ((1 << g.th) - 1) | (((1 << g.tw) - 1) << 8); return; }
     // taps a with 0 <= iy0 + a*ts < IH form a contiguous range [lo, hi]
     const int ylo = g.ts > 0 ? 0 : max(0, iy0 - g.IH + 1), yhi = g.ts > 0 ? min(g.th, g.IH - iy0) - 1 : min(g.th - 1, iy0);
     const int xlo = g.ts > 0 ? 0 : max(0, ix0 - g.IW + 1), xhi = g.ts > 0 ? min(g.tw, g.IW - ix0) - 1 : min(g.tw - 1, ix0);
@@ -155,12 +158,24 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
   uint64_t* tfull_bar = empty_bar + STAGES;          // [2] accumulator ready for the epilogue
   uint64_t* tempty_bar = tfull_bar + 2;              // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // (element offset of the tap + channel chunk, tap bit pair) of every 16-byte chunk of every k-block: decoded ONCE per CTA instead of once
+  // per thread and k-block (two multiply-high divisions + a dozen integer operations in the gather warps' inner loop, which is issue-bound)
+  int2* s_ktab = reinterpret_cast<int2*>(smem + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nkb = p.num_kb;
   const int tiles_n = (p.N + BN - 1) / BN;
   const long long tiles = ((p.g.rows + CV_BM - 1) / CV_BM) * tiles_n;
+  const bool use_ktab = nkb <= CVF_KTAB_KB;
+  if (use_ktab) {
+    for (int i = threadIdx.x; i < nkb * 8; i += CVF_THREADS) {
+      const int kidx = (i >> 3) * CV_BK + (i & 7) * 8;
+      int a, b, c;
+      decode_k(p.g, kidx, a, b, c);
+      s_ktab[i] = make_int2((a * p.g.IW + b) * p.g.ts * p.g.C + c, kidx < p.g.K ? ((1 << a) | (256 << b)) : 0x10000);
+    }
+  }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
@@ -243,11 +258,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
       for (int i = 0; i < 4; ++i) row_state(g, m0 + rg + 32 * i, rhw, off[i], mask[i]);
       for (int kb = 0; kb < nkb; ++kb, ++gs) {
         mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 32);
-        const int kidx = kb * CV_BK + j * 8;
-        int a, b, c;
-        decode_k(g, kidx, a, b, c);
-        const int koff = (a * g.IW + b) * g.ts * g.C + c;
-        const int kbit = kidx < g.K ? ((1 << a) | (256 << b)) : 0x10000;       // bit 16 is never set in a row mask
+        int koff, kbit;
+        if (use_ktab) {
+          const int2 kt = s_ktab[kb * 8 + j];
+          koff = kt.x; kbit = kt.y;
+        } else {
+          const int kidx = kb * CV_BK + j * 8;
+          int a, b, c;
+          decode_k(g, kidx, a, b, c);
+          koff = (a * g.IW + b) * g.ts * g.C + c;
+          kbit = kidx < g.K ? ((1 << a) | (256 << b)) : 0x10000;       // bit 16 is never set in a row mask
+        }
         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES) + dst_off;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -280,28 +301,64 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const ConvFwdParams p) 
       const bool row_ok = row < g.rows;
       long long n = 0; int yy = 0, xx = 0;
       if (row_ok) decode_row(g, row, rhw, n, yy, xx);
+      const long long obase = p.ncls > 1 ? (n * p.OH + 2 * yy) * p.OW + 2 * xx : (n * p.OH + yy) * p.OW + xx;      // output pixel of class 0
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         if (n0 + cc >= p.N) break;
         uint32_t v[32];
         tmem_ld32(acc + (uint32_t)cc, v);
         if (!row_ok) continue;
+        if (p.ncls == 1 && p.out_mode == 0 && (p.Cout & 7) == 0 && p.Cpad == p.Cout && p.OH == g.RH && p.OW == g.RW) {
+          // plain NHWC rows (gather form): output row = GEMM row, 8-channel groups are 16-byte aligned
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.Cout + n0 + cc;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int col = n0 + cc + 8 * h;
-          if (col >= p.N || cc + 8 * h >= BN) continue;
-          const int cls = col / p.Cpad;
-          const int co0 = col - cls * p.Cpad;
+          for (int h = 0; h < 4; ++h) {
+            if (n0 + cc + 8 * h >= p.Cout || cc + 8 * h >= BN) continue;
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * h + q]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] += __ldg(p.bias + n0 + cc + 8 * h + q);
+            }
+            uint4 pk;
+            __nv_bfloat162 a0 = __floats2bfloat162_rn(f[0], f[1]), a1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(f[4], f[5]), a3 = __floats2bfloat162_rn(f[6], f[7]);
+            pk.x = *reinterpret_cast<uint32_t*>(&a0); pk.y = *reinterpret_cast<uint32_t*>(&a1);
+            pk.z = *reinterpret_cast<uint32_t*>(&a2); pk.w = *reinterpret_cast<uint32_t*>(&a3);
+            *reinterpret_cast<uint4*>(orow + 8 * h) = pk;
+          }
+          continue;
+        }
+        // generic path (sub-pixel classes stacked along N, NCHW fp32 output, ragged channel counts): class / channel of the chunk's first
+        // column by ONE division, then carried incrementally over the four 8-column groups (Cpad is a multiple of 8); the pixel index of
+        // class 0 is computed once per tile (obase)
+        int cls = (n0 + cc) / p.Cpad;
+        int co0 = (n0 + cc) - cls * p.Cpad;
+#pragma unroll
+        for (int h = 0; h < 4; ++h, co0 += 8) {
+          if (n0 + cc + 8 * h >= p.N || cc + 8 * h >= BN) continue;
+          if (co0 >= p.Cpad) { co0 -= p.Cpad; ++cls; }
           const int nco = min(8, p.Cout - co0);
           if (nco <= 0) continue;
           int oy = yy, ox = xx;
-          if (p.ncls > 1) { oy = 2 * yy + (cls >> 1); ox = 2 * xx + (cls & 1); }
+          long long pix = obase;
+          if (p.ncls > 1) { oy = 2 * yy + (cls >> 1); ox = 2 * xx + (cls & 1); pix += (long long)(cls >> 1) * p.OW + (cls & 1); }
           if (oy >= p.OH || ox >= p.OW) continue;
           float f[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * h + q]) + ((p.bias != nullptr && q < nco) ? __ldg(p.bias + co0 + q) : 0.f);
+          for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[8 * h + q]);
+          if (p.bias != nullptr) {
+            if (nco == 8) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) f[q] += __ldg(p.bias + co0 + q);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) if (q < nco) f[q] += __ldg(p.bias + co0 + q);
+            }
+          }
           if (p.out_mode == 0) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ((n * p.OH + oy) * p.OW + ox) * p.Cout + co0;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + co0;
             if (nco == 8 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
               uint4 pk;
               __nv_bfloat162 a0 = __floats2bfloat162_rn(f[0], f[1]), a1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -569,7 +626,7 @@ __global__ void __launch_bounds__(256) u8_nchw_to_nhwc8_kernel(const uint8_t* __
 template <int BN>
 static int launch_fwd(const CUtensorMap& tw, const ConvFwdParams& p, cudaStream_t st) {
   constexpr int STAGES = FwdCfg<BN>::STAGES;
-  constexpr int SMEM = STAGES * (CV_BM + BN) * CV_BK * 2 + 1024 + 256;
+  constexpr int SMEM = STAGES * (CV_BM + BN) * CV_BK * 2 + 1024 + 256 + CVF_KTAB_KB * 8 * 8;
   static bool attr_set = false;
   static int ctas_per_sm = 1, sms = 148;
   auto kern = conv_fwd_kernel<BN, STAGES>;
@@ -613,6 +670,7 @@ static int fill_geom(ConvGeom* g, const void* in, int Nimg, int IH, int IW, int 
   g->m_rw = div_magic(RH * RW, RW);
   g->m_c = div_magic(g->K + 64 + 256, C);
   g->m_tw = div_magic(th * tw + 64, tw);
+  g->all_inside = (ts > 0 && (long long)(RH - 1) * sy + th <= IH && (long long)(RW - 1) * sy + tw <= IW) ? 1 : 0;
   return 0;
 }
 
