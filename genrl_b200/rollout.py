@@ -5,14 +5,18 @@ The op-level path builds the rollout out of ~45 autograd nodes per step: concate
 [stoch | deter], dtype casts, `torch.stack` of the per-step lists, and — in the backward — autograd's own gradient-accumulation adds.
 Here the H steps run over pre-laid-out buffers:
 
-  feat  [H+1, N, S*K + D]   compute dtype   the categorical sampler writes its one-hot straight into feat[i][:, :S*K], the GRU gate kernel
-                                            writes deter straight into feat[i][:, S*K:]; every consumer GEMM takes (pointer, leading dim)
+  slab  [H+1, N, a0 + S*K + D + Hd]   compute dtype   one row per (step, sample): [ action_{i+1} (padded to a0) | stoch_i | deter_i | x_{i+1} ].
+                                            The actor reads feat_i = [stoch | deter], the input block [action | stoch], the GRU GEMM [deter | x]
+                                            — column windows of the same row (pointer + leading dimension), with W_in / W_gru column-permuted
+                                            once per call; the sampler, the GRU gate kernel, the actor head and the input block's chain kernel
+                                            write straight into their ranges, so no copy kernel runs between the steps
   stoch / deter / logit / action [H+1, N, .] fp32   the API's `seq` entries, written in place by the same kernels (no torch.stack)
   per-step saved tensors (pre-LayerNorm activations, statistics, GRU pre-activations, head outputs, noise) in [H, N, .] slabs
 
-and the backward is the hand-sequenced reverse loop: gradient sums are fused into accumulate-epilogues of the dgrad GEMMs / the linear
-straight-through backward, the actor's weight gradients are ONE GEMM per layer over all H*N rows (the slabs are already contiguous),
-nothing goes through autograd inside the rollout.  20 launches per step forward instead of ~45, no ATen kernels.
+The backward is the hand-sequenced reverse loop over the recurrence only: gradient sums are folded into the GRU backward kernel (up to four
+sources summed on the fly).  The actor reads sg(feat_{i-1}), so nothing in the recurrence depends on its backward: it runs ONCE over all H*N
+rows after the loop (head, per layer one LayerNorm backward incl. parameter gradients, one dgrad and one wgrad GEMM at 36 000 rows).
+Nothing goes through autograd inside the rollout.  ~11 launches per step forward instead of ~45, no ATen kernels.
 
 Gradients flow out of `feat`, `stoch` and `policy_ent` (the only rollout outputs a GenRL loss reads: dreamer.py:392-438,
 tools/genrl_utils.py:250-277) into the ACTOR's parameters; the world model is frozen inside the behaviour update (dreamer.py:376-384) and
