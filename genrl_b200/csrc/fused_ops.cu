@@ -361,53 +361,136 @@ __device__ __forceinline__ void cat_probs_bwd_thr(const float (&p)[CK], const fl
   for (int k = 0; k < CK; ++k) dl[k] = p[k] * (dl[k] - dot2);
 }
 
+// ---- four lanes per latent (K == 32: 8 classes per lane) ------------------------------------------------------------------------------------
+// A thread-per-latent kernel reads / writes 128 contiguous bytes per THREAD (32 lines per warp instruction) and run 8 Philox calls and
+// 32 logarithms in one dependent chain; at the rollout's 2 400 rows that is 17 us per launch.  Here a quad of lanes shares one latent: loads and
+// stores are coalesced (a warp covers 8 latents = 1 KB), each lane does 2 Philox calls.  Sums run in the SAME sequential class order as the
+// thread kernels (lane 0 adds its 8 values, hands the partial to lane 1, ...), so probabilities, noise mapping and the sampled index are
+// bit-identical to the thread-per-latent form (cat_probs_thr, still used by the KL kernels and the generic backward).
+__device__ __forceinline__ float quad_seq_sum(const float (&v)[8], int ql, int lane) {
+  float acc = 0.f;
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    if (ql == step) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += v[k];
+    }
+    acc = __shfl_sync(0xffffffffu, acc, (lane & ~3) + step);
+  }
+  return acc;
+}
+__device__ __forceinline__ float quad_seq_dot(const float (&a)[8], const float (&b)[8], int ql, int lane) {
+  float acc = 0.f;
+#pragma unroll
+  for (int step = 0; step < 4; ++step) {
+    if (ql == step) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += a[k] * b[k];
+    }
+    acc = __shfl_sync(0xffffffffu, acc, (lane & ~3) + step);
+  }
+  return acc;
+}
+__device__ __forceinline__ void cat_probs_quad(const float* __restrict__ lg8, float (&p)[8], float (&pi)[8], float& usum, int ql, int lane) {
+  const float4 v0 = reinterpret_cast<const float4*>(lg8)[0], v1 = reinterpret_cast<const float4*>(lg8)[1];
+  p[0] = v0.x; p[1] = v0.y; p[2] = v0.z; p[3] = v0.w; p[4] = v1.x; p[5] = v1.y; p[6] = v1.z; p[7] = v1.w;
+  float mx = p[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, p[k]);
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#pragma unroll
+  for (int k = 0; k < 8; ++k) p[k] = expf(p[k] - mx);
+  const float s = quad_seq_sum(p, ql, lane);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { p[k] = p[k] / s; pi[k] = 0.99f * p[k] + 0.01f / CK; }
+  const float us = quad_seq_sum(pi, ql, lane);
+  usum = us;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) pi[k] = pi[k] / us;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(128) cat_sample_fwd_thr_kernel(const float* __restrict__ logit, const float* __restrict__ noise,
-                                                                 unsigned long long seed, unsigned long long offset,
-                                                                 const unsigned long long* __restrict__ step_dev, int sample,
-                                                                 T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
-                                                                 long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S) {
+__global__ void __launch_bounds__(128) cat_sample_fwd_quad_kernel(const float* __restrict__ logit, const float* __restrict__ noise,
+                                                                  unsigned long long seed, unsigned long long offset,
+                                                                  const unsigned long long* __restrict__ step_dev, int sample,
+                                                                  T* __restrict__ stoch, long long ld_stoch, float* __restrict__ stoch32,
+                                                                  long long ld_stoch32, int* __restrict__ idx_out, long long rows, int S) {
   genrl::pdl_sync();
-  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
-  if (g >= rows * S) return;
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31, ql = threadIdx.x & 3;
+  const bool active = (t >> 2) < rows * S;
+  const long long g = active ? (t >> 2) : 0;                  // inactive quads compute on latent 0 and store nothing (full-warp shuffles)
   if (step_dev) seed += *step_dev * 0x9E3779B97F4A7C15ull;
-  float p[CK], pi[CK], usum;
-  cat_probs_thr(logit + g * CK, p, pi, usum);
+  float p[8], pi[8], usum;
+  cat_probs_quad(logit + g * CK + ql * 8, p, pi, usum, ql, lane);
   float best = -INFINITY; int bi = 0;
   if (sample) {
 #pragma unroll
-    for (int j = 0; j < CK / 4; ++j) {
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = ql * 2 + jj;
       float q[4];
-      if (noise) { float4 v = reinterpret_cast<const float4*>(noise + g * CK)[j]; q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
+      if (noise) { const float4 v = reinterpret_cast<const float4*>(noise + g * CK)[j]; q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w; }
       else {
         const unsigned long long c = (unsigned long long)g * (CK / 4) + j;
-        uint4 r = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint4 r = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
         q[0] = -logf(u32_to_unit_open(r.x)); q[1] = -logf(u32_to_unit_open(r.y)); q[2] = -logf(u32_to_unit_open(r.z)); q[3] = -logf(u32_to_unit_open(r.w));
       }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { float sc = pi[4 * j + e] / q[e]; if (sc > best) { best = sc; bi = 4 * j + e; } }
+      for (int e = 0; e < 4; ++e) { const float sc = pi[4 * jj + e] / q[e]; if (sc > best) { best = sc; bi = ql * 8 + 4 * jj + e; } }
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < CK; ++k) { float sc = logf(pi[k]); if (sc > best) { best = sc; bi = k; } }
+    for (int k = 0; k < 8; ++k) { const float sc = logf(pi[k]); if (sc > best) { best = sc; bi = ql * 8 + k; } }
   }
+  // first maximum in class order: on ties the lower class index wins (what the sequential strict-'>' scan of the thread kernel picks)
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (!active) return;
   const long long row = g / S; const int sidx = (int)(g % S);
-  float oh[CK];
+  float oh[8];
 #pragma unroll
-  for (int k = 0; k < CK; ++k) oh[k] = k == bi ? 1.f : 0.f;
+  for (int k = 0; k < 8; ++k) oh[k] = (ql * 8 + k) == bi ? 1.f : 0.f;
   if (stoch32) {
-    float4* o = reinterpret_cast<float4*>(stoch32 + row * ld_stoch32 + sidx * CK);
-#pragma unroll
-    for (int i = 0; i < CK / 4; ++i) o[i] = make_float4(oh[4 * i], oh[4 * i + 1], oh[4 * i + 2], oh[4 * i + 3]);
+    float4* o = reinterpret_cast<float4*>(stoch32 + row * ld_stoch32 + sidx * CK + ql * 8);
+    o[0] = make_float4(oh[0], oh[1], oh[2], oh[3]); o[1] = make_float4(oh[4], oh[5], oh[6], oh[7]);
   }
-  if (stoch) {
+  if (stoch) V8<T>::store(stoch + row * ld_stoch + sidx * CK + ql * 8, oh);
+  if (idx_out && ql == 0) idx_out[g] = bi;
+}
+
+// rollout backward: two gradient contributions (the feat slice of step i and the next step's input projection) summed on the fly, the logit
+// gradient written in the activation dtype so that it is the dgrad GEMM's A operand as is (no accumulate pass, no cast pass)
+template <typename T>
+__global__ void __launch_bounds__(128) cat_sample_bwd2_quad_kernel(const float* __restrict__ logit, const T* __restrict__ ds1, long long ld1,
+                                                                   const T* __restrict__ ds2, long long ld2, T* __restrict__ dl_out, long long ld_dl,
+                                                                   long long rows, int S) {
+  genrl::pdl_sync();
+  const long long t = (long long)blockIdx.x * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31, ql = threadIdx.x & 3;
+  const bool active = (t >> 2) < rows * S;
+  const long long g = active ? (t >> 2) : 0;
+  float p[8], pi[8], usum, dpi[8], dl[8];
+  cat_probs_quad(logit + g * CK + ql * 8, p, pi, usum, ql, lane);
+  const long long row = g / S; const int sidx = (int)(g % S);
+  V8<T>::load(ds1 + row * ld1 + sidx * CK + ql * 8, dpi);
+  if (ds2) {
+    float v8[8];
+    V8<T>::load(ds2 + row * ld2 + sidx * CK + ql * 8, v8);
 #pragma unroll
-    for (int i = 0; i < CK / 8; ++i) { float v8[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v8[e] = oh[8 * i + e];
-      V8<T>::store(stoch + row * ld_stoch + sidx * CK + 8 * i, v8); }
+    for (int e = 0; e < 8; ++e) dpi[e] += v8[e];
   }
-  if (idx_out) idx_out[g] = bi;
+  const float dot = quad_seq_dot(dpi, pi, ql, lane);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dl[k] = 0.99f * (dpi[k] - dot) / usum;
+  const float dot2 = quad_seq_dot(dl, p, ql, lane);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dl[k] = p[k] * (dl[k] - dot2);
+  if (active) V8<T>::store(dl_out + row * ld_dl + sidx * CK + ql * 8, dl);
 }
 
 template <typename T>
@@ -430,40 +513,6 @@ __global__ void __launch_bounds__(128) cat_sample_bwd_thr_kernel(const float* __
     float4 v = make_float4(dl[4 * i], dl[4 * i + 1], dl[4 * i + 2], dl[4 * i + 3]);
     if (accumulate) { float4 a = o[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
     o[i] = v;
-  }
-}
-
-// rollout backward: two gradient contributions (the feat slice of step i and the next step's input projection) summed on the fly, the logit
-// gradient written in the activation dtype so that it is the dgrad GEMM's A operand as is (no accumulate pass, no cast pass)
-template <typename T>
-__global__ void __launch_bounds__(128) cat_sample_bwd2_thr_kernel(const float* __restrict__ logit, const T* __restrict__ ds1, long long ld1,
-                                                                  const T* __restrict__ ds2, long long ld2, T* __restrict__ dl_out, long long ld_dl,
-                                                                  long long rows, int S) {
-  genrl::pdl_sync();
-  const long long g = (long long)blockIdx.x * 128 + threadIdx.x;
-  if (g >= rows * S) return;
-  float p[CK], pi[CK], usum, dpi[CK], dl[CK];
-  cat_probs_thr(logit + g * CK, p, pi, usum);
-  const long long row = g / S; const int sidx = (int)(g % S);
-#pragma unroll
-  for (int i = 0; i < CK / 8; ++i) {
-    float v8[8];
-    V8<T>::load(ds1 + row * ld1 + sidx * CK + 8 * i, v8);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) dpi[8 * i + e] = v8[e];
-    if (ds2) {
-      V8<T>::load(ds2 + row * ld2 + sidx * CK + 8 * i, v8);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) dpi[8 * i + e] += v8[e];
-    }
-  }
-  cat_probs_bwd_thr(p, pi, usum, dpi, dl);
-#pragma unroll
-  for (int i = 0; i < CK / 8; ++i) {
-    float v8[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v8[e] = dl[8 * i + e];
-    V8<T>::store(dl_out + row * ld_dl + sidx * CK + 8 * i, v8);
   }
 }
 
@@ -1116,8 +1165,8 @@ extern "C" int genrl_cat_sample_fwd(void* stream, const float* logit, const floa
   if (fast_ok) {
     DISPATCH_T(dtype, {
       if (!stoch || vec_ok<T>(stoch, ld_stoch)) {
-        genrl::launch_pdl(cat_sample_fwd_thr_kernel<T>, ceil_div(rows * S, 128), 128, 0, ST(stream), logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
-                                                                                     stoch32, ld_stoch32, idx, rows, S);
+        genrl::launch_pdl(cat_sample_fwd_quad_kernel<T>, ceil_div(rows * S * 4, 128), 128, 0, ST(stream), logit, noise, seed, offset, step_dev, sample, (T*)stoch, ld_stoch,
+                                                                                      stoch32, ld_stoch32, idx, rows, S);
         return check_launch("cat_sample_fwd");
       }
     });
@@ -1150,7 +1199,7 @@ extern "C" int genrl_cat_sample_bwd2(void* stream, const float* logit, const voi
   GENRL_REQUIRE(K == CK && f32_vec_ok(logit), "cat_sample_bwd2: K must be %d and logit 16-byte aligned", CK);
   DISPATCH_T(dtype, {
     GENRL_REQUIRE(vec_ok<T>(ds1, ld1) && (!ds2 || vec_ok<T>(ds2, ld2)) && vec_ok<T>(dlogit, ld_dl), "cat_sample_bwd2: operands must be 16-byte aligned");
-    genrl::launch_pdl(cat_sample_bwd2_thr_kernel<T>, ceil_div(rows * S, 128), 128, 0, ST(stream), logit, (const T*)ds1, ld1, (const T*)ds2, ld2, (T*)dlogit, ld_dl, rows, S);
+    genrl::launch_pdl(cat_sample_bwd2_quad_kernel<T>, ceil_div(rows * S * 4, 128), 128, 0, ST(stream), logit, (const T*)ds1, ld1, (const T*)ds2, ld2, (T*)dlogit, ld_dl, rows, S);
   });
   return check_launch("cat_sample_bwd2");
 }
