@@ -225,6 +225,10 @@ def run_native(args):
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
+        # The four gradient all-reduces (219 MB) sit on the critical path; with NCCL's default CTA count they run at ~330 GB/s on 2 GPUs.
+        # Measured (profiles/r02_notes.md §24): NCCL_MIN_CTAS=32 takes the 2-GPU step from 21.0 to 20.4 ms and is neutral on 8 GPUs (NVLS already
+        # uses 24-32 channels).  An explicit setting in the environment wins.
+        os.environ.setdefault("NCCL_MIN_CTAS", "32")
         try:
             dist.init_process_group("nccl", device_id=torch.device(dev))
             t = torch.zeros(1, device=dev)
