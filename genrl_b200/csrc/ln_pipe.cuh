@@ -6,13 +6,14 @@
 // 4-5 warps per issue, 18-31 % of HBM bandwidth; 124-133 us for 38 400 x 1024 where the bytes need 36 us).  The first staged attempt of this
 // round (removed) loaded a tile, waited, and recomputed the SiLU-gradient math in both of its passes: twice the instructions, no overlap.
 // Here
-//   * one elected warp streams row tiles (R rows of dy and x, 64 KB) into a two-stage shared-memory ring with cp.async.bulk and an
+//   * one elected warp streams row tiles (R rows of dy and x, 32 KB) into a two-stage shared-memory ring with cp.async.bulk and an
 //     mbarrier per stage: the next tile is in flight while the current one is computed, no register is tied up by a load;
-//   * phase 1 (warp per row, 16 warps): g = dy * act'(a) ONCE per element, row sums c1 = mean(g gamma), c2 = mean(g gamma xhat); g is parked
+//     256 threads x 2 blocks per SM, so that one block computes while the other sits in a row reduction or a barrier;
+//   * phase 1 (warp per row, 8 warps per block): g = dy * act'(a) ONCE per element, row sums c1 = mean(g gamma), c2 = mean(g gamma xhat); g is parked
 //     in shared memory as fp32 (two 16-byte planes: conflict-free for both phases);
 //   * phase 2 (thread per 8-column chunk, fixed for the whole launch): dx = rstd (g gamma - c1 - xhat c2) with 16-byte coalesced stores and
-//     the chunk's dgamma / dbeta / dbias partials in 24 registers — no recomputation of the activation gradient, ~26 instructions per
-//     element in total at 16 warps per SM;
+//     the chunk's dgamma / dbeta / dbias partials in 24 registers — no recomputation of the activation gradient (measured: 33 instructions
+//     per element in total, issue slots ~60 % busy at 16 warps per SM);
 //   * column partials leave the block once, as fp32 atomics.
 // HBM traffic is the minimum: dy and x read once, dx written once.
 #pragma once
@@ -68,7 +69,7 @@ __device__ __forceinline__ void lnp_issue(const T* __restrict__ a, long long lda
 // Geometry (all compile-time: D = 8 * LPR * CPL, so every loop unrolls and every shared-memory offset is a 32-bit constant expression).
 //   LPR  lanes per row in the warp-per-row phase (power of two), CPL chunks of 8 elements per lane:
 //        1024 = (32,4)  512 = (32,2)  256 = (32,1)  384 = (16,3)  192 = (8,3)  96 = (4,3)  48 = (2,3)   (the MLP width and the conv channel counts)
-//   rows per tile R: a multiple of the phase-2 row groups (512 threads / chunks per row) that also fills the 16 * 32 / LPR phase-1 row slots
+//   rows per tile R: a multiple of the phase-2 row groups (256 threads / chunks per row) that also fills the 8 * 32 / LPR phase-1 row slots
 template <typename T, int LPR, int CPL> struct LnpGeom {
   static constexpr int D = 8 * LPR * CPL;
   static constexpr int CPR = LPR * CPL;                       // 8-element chunks per row
