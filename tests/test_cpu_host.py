@@ -40,6 +40,16 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    # round 2: 2-CTA tensor-core instructions (cta_group::2), 1-D bulk copies of the LayerNorm pipelines, cluster barriers of the chain kernel
+    assert "UTCHMMA.2CTA" in sass and "UBLKCP" in sass and "UCGABAR" in sass
+
+
+def test_streaming_scan_eligibility_is_a_pure_shape_query():
+    """genrl_rssm_scan_stream_supported launches nothing: BASELINE configs[4]'s shard (16 sequences, deter 4096) is eligible, more than 16
+    sequences, widths that are not multiples of 128 and widths needing more than 160 CTAs are not"""
+    f = lib.load().genrl_rssm_scan_stream_supported
+    assert f(16, 4096) == 1 and f(1, 1280) == 1 and f(16, 2048) == 1
+    assert f(17, 4096) == 0 and f(16, 4000) == 0 and f(0, 4096) == 0 and f(16, 8192) == 0
 
 
 @pytest.mark.parametrize("case", ["tiny_genrl", "tiny_dreamer"])
